@@ -1,0 +1,69 @@
+// Shared device/host helpers for libfar_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/far_sm100.h"
+
+#define FAR_CHECK_LAUNCH()                                                      \
+  do {                                                                          \
+    cudaError_t _e = cudaGetLastError();                                        \
+    if (_e != cudaSuccess) {                                                    \
+      fprintf(stderr, "[far_sm100] %s:%d launch failed: %s\n", __FILE__, __LINE__, \
+              cudaGetErrorString(_e));                                          \
+      return FAR_ERR_CUDA;                                                      \
+    }                                                                           \
+  } while (0)
+
+#define FAR_REQUIRE(cond)                                                       \
+  do {                                                                          \
+    if (!(cond)) {                                                              \
+      fprintf(stderr, "[far_sm100] %s:%d bad argument: %s\n", __FILE__, __LINE__, #cond); \
+      return FAR_ERR_ARG;                                                       \
+    }                                                                           \
+  } while (0)
+
+namespace far {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// activation codes of the C-ABI (include/far_sm100.h)
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case FAR_ACT_RELU: return fmaxf(x, 0.f);
+    case FAR_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));  // exact-erf nn.GELU
+    case FAR_ACT_ELU1: return x > 0.f ? x + 1.f : expm1f(x) + 1.f;                   // F.elu(x) + 1
+    case FAR_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+    default: return x;
+  }
+}
+
+// online log-sum-exp pair (m = running max, s = sum of exp(x - m))
+struct MS {
+  float m, s;
+};
+__device__ __forceinline__ MS ms_init() { return MS{-INFINITY, 0.f}; }
+__device__ __forceinline__ MS ms_merge(MS a, MS b) {
+  float m = fmaxf(a.m, b.m);
+  if (m == -INFINITY) return MS{m, 0.f};
+  return MS{m, a.s * expf(a.m - m) + b.s * expf(b.m - m)};
+}
+
+}  // namespace far

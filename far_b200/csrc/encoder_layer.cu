@@ -1,0 +1,73 @@
+// LoFTREncoderLayer.forward (mp3d_loftr/src/loftr/loftr_module/transformer.py:44-67), masks None.
+// Host-side composition of the library's own kernels so the Python side makes one C-ABI call per layer.
+#include "common.cuh"
+
+namespace far {
+int linear_dispatch(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
+                    const float* bias, float* y, int ldy, int M, int N, int act, int act_cols, int engine,
+                    float* workspace, size_t workspace_bytes, cudaStream_t st);
+int linear_attention_dispatch(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out,
+                              int ldo, int N, int L, int S, int H, int D, float eps, int applied, float* workspace,
+                              size_t workspace_bytes, cudaStream_t st);
+size_t linear_attention_ws_bytes(int N, int S, int H, int D);
+
+static inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct LayerPlan {
+  size_t q, k, v, attn, msg, hid, la, total;
+};
+static LayerPlan plan_layer(long long N, int L, int S, int C, int nhead) {
+  LayerPlan p;
+  size_t off = 0;
+  const size_t rowsL = (size_t)N * L, rowsS = (size_t)N * S;
+  p.q = off; off += align_up(rowsL * C * 4);
+  p.k = off; off += align_up(rowsS * C * 4);
+  p.v = off; off += align_up(rowsS * C * 4);
+  p.attn = off; off += align_up(rowsL * C * 4);
+  p.msg = off; off += align_up(rowsL * C * 4);
+  p.hid = off; off += align_up(rowsL * 2 * C * 4);
+  p.la = off; off += align_up(linear_attention_ws_bytes((int)N, S, nhead, C / nhead));
+  p.total = off;
+  return p;
+}
+}  // namespace far
+
+using namespace far;
+
+extern "C" size_t far_loftr_encoder_layer_workspace_bytes(int N, int L, int S, int C, int nhead) {
+  return plan_layer(N, L, S, C, nhead).total + 256;
+}
+
+extern "C" int far_loftr_encoder_layer(const float* x, const float* source, float* out, int N, int L, int S, int C,
+                                       int nhead, const far_encoder_layer_weights* w, int engine, float* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  if (N <= 0 || L <= 0) return FAR_OK;
+  FAR_REQUIRE(x && source && out && w && workspace && C % nhead == 0 && C % 4 == 0);
+  const LayerPlan p = plan_layer(N, L, S, C, nhead);
+  if (workspace_bytes < p.total) return FAR_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = reinterpret_cast<char*>(workspace);
+  float* q = reinterpret_cast<float*>(base + p.q);
+  float* k = reinterpret_cast<float*>(base + p.k);
+  float* v = reinterpret_cast<float*>(base + p.v);
+  float* attn = reinterpret_cast<float*>(base + p.attn);
+  float* msg = reinterpret_cast<float*>(base + p.msg);
+  float* hid = reinterpret_cast<float*>(base + p.hid);
+  float* la = reinterpret_cast<float*>(base + p.la);
+  const int ML = N * L, MS = N * S, D = C / nhead;
+  int rc;
+  // q/k projections with the elu(x)+1 feature map fused into the epilogue; v plain (:55-57, linear_attention.py:33-34)
+  if ((rc = linear_dispatch(x, C, C, nullptr, 0, 0, w->wq, C, nullptr, q, C, ML, C, FAR_ACT_ELU1, -1, engine, nullptr, 0, st))) return rc;
+  if ((rc = linear_dispatch(source, C, C, nullptr, 0, 0, w->wk, C, nullptr, k, C, MS, C, FAR_ACT_ELU1, -1, engine, nullptr, 0, st))) return rc;
+  if ((rc = linear_dispatch(source, C, C, nullptr, 0, 0, w->wv, C, nullptr, v, C, MS, C, FAR_ACT_NONE, -1, engine, nullptr, 0, st))) return rc;
+  if ((rc = linear_attention_dispatch(q, C, k, C, v, C, attn, C, N, L, S, nhead, D, 1e-6f, 1, la,
+                                      workspace_bytes - p.la, st))) return rc;
+  // merge + norm1 (:58-59)
+  if ((rc = linear_dispatch(attn, C, C, nullptr, 0, 0, w->wmerge, C, nullptr, msg, C, ML, C, FAR_ACT_NONE, -1, engine, nullptr, 0, st))) return rc;
+  if ((rc = far_layernorm(msg, w->g1, w->b1, nullptr, attn, ML, C, 1e-5f, stream))) return rc;  // attn := LN(msg)
+  // mlp([x | message]) (:62-63): two K-segments instead of a materialised concat
+  if ((rc = linear_dispatch(x, C, C, attn, C, C, w->wmlp0, 2 * C, nullptr, hid, 2 * C, ML, 2 * C, FAR_ACT_RELU, -1, engine, nullptr, 0, st))) return rc;
+  if ((rc = linear_dispatch(hid, 2 * C, 2 * C, nullptr, 0, 0, w->wmlp2, 2 * C, nullptr, msg, C, ML, C, FAR_ACT_NONE, -1, engine, nullptr, 0, st))) return rc;
+  // norm2 + residual (:64-66)
+  return far_layernorm(msg, w->g2, w->b2, x, out, ML, C, 1e-5f, stream);
+}

@@ -1,0 +1,340 @@
+// nn.Linear family, LayerNorm(+residual), positional-encoding flatten, FAR blend epilogue.
+#include "gemm_tile.cuh"
+#include "tc_gemm.cuh"
+
+namespace far {
+
+struct LinearArgs {
+  const float* x1; int ldx1; int K1;
+  const float* x2; int ldx2; int K2;
+  const float* W; int ldw;
+  const float* bias;
+  float* y; int ldy;
+  int M, N;
+  int act, act_cols;
+  float* ws;      // split-K partials [splits][M][N] (splits > 1)
+  int splits;
+  int kchunk;     // K1 range per split (multiple of TBK)
+  const float* rowbias;  // optional [ceil(M/rowbias_group)][N]: y[r] += rowbias[r / rowbias_group]
+  int rowbias_group;
+};
+
+template <bool kVec4>
+__global__ void __launch_bounds__(kTileThreads, 2) linear_simt_kernel(LinearArgs p) {
+  __shared__ TileSmem sm;
+  const int n0 = blockIdx.x * TBN, m0 = blockIdx.y * TBM, z = blockIdx.z;
+  const int mValid = min(TBM, p.M - m0), nValid = min(TBN, p.N - n0);
+  float acc[8][8];
+  tile_zero(acc);
+
+  int kbeg = 0, klen = p.K1;
+  if (p.splits > 1) {
+    kbeg = z * p.kchunk;
+    klen = min(p.kchunk, p.K1 - kbeg);
+    if (klen < 0) klen = 0;
+  }
+  simt_tile_mma<kVec4>(p.x1 + (size_t)m0 * p.ldx1 + kbeg, p.ldx1, mValid, p.W + (size_t)n0 * p.ldw + kbeg, p.ldw,
+                       nValid, klen, sm, acc);
+  if (p.x2 != nullptr && p.K2 > 0)
+    simt_tile_mma<kVec4>(p.x2 + (size_t)m0 * p.ldx2, p.ldx2, mValid, p.W + (size_t)n0 * p.ldw + p.K1, p.ldw,
+                         nValid, p.K2, sm, acc);
+
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  if (p.splits > 1) {
+    float* out = p.ws + (size_t)z * p.M * p.N;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = m0 + tile_row(ty, i);
+      if (r >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = n0 + tile_col(tx, j);
+        if (c < p.N) out[(size_t)r * p.N + c] = acc[i][j];
+      }
+    }
+    return;
+  }
+  const int actc = p.act_cols < 0 ? p.N : p.act_cols;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = m0 + tile_row(ty, i);
+    if (r >= p.M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int c0 = n0 + tile_col(tx, jh * 4);
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j;
+        float t = acc[i][jh * 4 + j];
+        if (c < p.N) {
+          if (p.bias) t += __ldg(p.bias + c);
+          if (p.rowbias) t += __ldg(p.rowbias + (size_t)(r / p.rowbias_group) * p.N + c);
+          if (c < actc) t = apply_act(t, p.act);
+        }
+        v[j] = t;
+      }
+      float* dst = p.y + (size_t)r * p.ldy + c0;
+      if (c0 + 3 < p.N && ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15u) == 0)) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c0 + j < p.N) dst[j] = v[j];
+      }
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ bias,
+                                     float* __restrict__ y, int ldy, int M, int N, int act, int act_cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * N) return;
+  const int r = (int)(idx / N), c = (int)(idx % N);
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += ws[(size_t)z * M * N + idx];  // fixed order: deterministic
+  if (bias) s += bias[c];
+  const int actc = act_cols < 0 ? N : act_cols;
+  if (c < actc) s = apply_act(s, act);
+  y[(size_t)r * ldy + c] = s;
+}
+
+static void choose_splits(int M, int N, int K, int* splits, int* kchunk) {
+  const int tiles = ceil_div(M, TBM) * ceil_div(N, TBN);
+  int s = 1;
+  if (tiles < kNumSMs && K >= 2048) {
+    s = (2 * kNumSMs) / tiles;
+    const int maxs = K / 256;  // at least 256 of K per split
+    if (s > maxs) s = maxs;
+    if (s < 1) s = 1;
+    if (s > 128) s = 128;
+  }
+  int kc = ceil_div(ceil_div(K, s), TBK) * TBK;
+  s = ceil_div(K, kc);
+  *splits = s;
+  *kchunk = kc;
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+// one warp per row, row cached in registers (C <= 1024), two-pass mean/variance like ATen's CPU kernel.
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ pre, int pre_rows,
+                                 const float* __restrict__ g, const float* __restrict__ b,
+                                 const float* __restrict__ res, float* __restrict__ y, int rows, int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (size_t)warp * C;
+  const float* pr = pre ? pre + (size_t)(warp % pre_rows) * C : nullptr;  // broadcast table (e.g. pos_embed)
+  float v[32];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + i * 32;
+    v[i] = (c < C) ? xr[c] + (pr ? pr[c] : 0.f) : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + i * 32;
+    const float d = (c < C) ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) {
+      float o = (v[i] - mean) * rstd * g[c] + b[c];
+      if (res) o += res[(size_t)warp * C + c];
+      y[(size_t)warp * C + c] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- pos-enc + flatten
+// out[n, hw, c] = feat[n,c,h,w] + pe[hw, c].  32x32 smem transpose when the input is NCHW (sw == 1);
+// straight coalesced copy when it is channels_last (sc == 1).
+__global__ void pos_flatten_kernel(const float* __restrict__ feat, long long sn, long long sc, long long sh,
+                                   long long sw, const float* __restrict__ pe, float* __restrict__ out, int C,
+                                   int H, int W) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32, HW = H * W;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const float* f = feat + (size_t)n * sn;
+  if (sc == 1) {
+    for (int r = ty; r < 32; r += 8) {
+      const int hw = hw0 + r, c = c0 + tx;
+      if (hw < HW && c < C) {
+        const int h = hw / W, w = hw % W;
+        out[((size_t)n * HW + hw) * C + c] = f[(size_t)h * sh + (size_t)w * sw + c] + pe[(size_t)hw * C + c];
+      }
+    }
+    return;
+  }
+  for (int r = ty; r < 32; r += 8) {  // r indexes channel, tx indexes hw (contiguous when sw == 1)
+    const int c = c0 + r, hw = hw0 + tx;
+    float v = 0.f;
+    if (c < C && hw < HW) {
+      const int h = hw / W, w = hw % W;
+      v = f[(size_t)c * sc + (size_t)h * sh + (size_t)w * sw];
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {  // r indexes hw, tx indexes channel
+    const int hw = hw0 + r, c = c0 + tx;
+    if (hw < HW && c < C) out[((size_t)n * HW + hw) * C + c] = tile[tx][r] + pe[(size_t)hw * C + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- FAR blend
+__global__ void pose_blend_mp3d_kernel(const float* __restrict__ pred, const float* __restrict__ solver, int lds,
+                                       const float* __restrict__ wt, const float* __restrict__ mean,
+                                       const float* __restrict__ stdv, int scale_8pt, float* __restrict__ out,
+                                       int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* p = pred + (size_t)b * 9;
+  const float* s = solver + (size_t)b * lds;
+  float ts[3] = {s[0], s[1], s[2]};
+  if (scale_8pt) {  // transformer.py:436-446
+    float lu[3], ru[3], nl = 0.f, nr = 0.f;
+    for (int i = 0; i < 3; ++i) {
+      lu[i] = s[i] * stdv[i] + mean[i];
+      ru[i] = p[i] * stdv[i] + mean[i];
+      nl += lu[i] * lu[i];
+      nr += ru[i] * ru[i];
+    }
+    nl = fminf(fmaxf(sqrtf(nl), 1e-3f), 100.f);
+    nr = sqrtf(nr);
+    for (int i = 0; i < 3; ++i) ts[i] = (lu[i] * nr / nl - mean[i]) / stdv[i];
+  }
+  const float w0 = wt[b * 2 + 0], w1 = wt[b * 2 + 1];
+  float* o = out + (size_t)b * 9;
+  for (int i = 0; i < 3; ++i) o[i] = w0 * p[i] + (1.f - w0) * ts[i];
+  for (int i = 3; i < 9; ++i) o[i] = w1 * p[i] + (1.f - w1) * s[i];
+}
+
+// Host-side dispatcher shared with the layer composition in encoder_layer.cu.
+int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
+                       const float* bias, const float* rowbias, int rowbias_group, float* y, int ldy, int M, int N,
+                       int act, int act_cols, int engine, float* workspace, size_t workspace_bytes, cudaStream_t st);
+
+int linear_dispatch(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
+                    const float* bias, float* y, int ldy, int M, int N, int act, int act_cols, int engine,
+                    float* workspace, size_t workspace_bytes, cudaStream_t st) {
+  return linear_dispatch_rb(x1, ldx1, K1, x2, ldx2, K2, W, ldw, bias, nullptr, 1, y, ldy, M, N, act, act_cols, engine,
+                            workspace, workspace_bytes, st);
+}
+
+// `rowbias` (fine_preprocess: the per-match coarse term broadcast over the 25 window positions) is only
+// implemented by the CUDA-core engine.
+int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
+                       const float* bias, const float* rowbias, int rowbias_group, float* y, int ldy, int M, int N,
+                       int act, int act_cols, int engine, float* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return FAR_OK;
+  FAR_REQUIRE(x1 && W && y && K1 > 0 && ldx1 >= K1 && ldw >= K1 + K2 && ldy >= N);
+  FAR_REQUIRE((x2 == nullptr) == (K2 == 0));
+
+  // tcgen05 3xTF32 engine: TMA needs contiguous-K rows with 16-byte-multiple strides.
+  const bool tc_ok = tc_linear_supported(x1, ldx1, K1, x2, ldx2, K2, W, ldw, M, N);
+  if (engine == 2 && (!tc_ok || rowbias)) return FAR_ERR_ARG;
+  if (!rowbias && (engine == 2 || (engine == 0 && tc_ok && tc_engine_default_on()))) {
+    return tc_linear(x1, ldx1, K1, x2, ldx2, K2, W, ldw, bias, y, ldy, M, N, act, act_cols, workspace,
+                     workspace_bytes, st);
+  }
+
+  LinearArgs p{x1, ldx1, K1, x2, ldx2, K2, W, ldw, bias, y, ldy, M, N, act, act_cols, nullptr, 1, K1, rowbias,
+               rowbias_group > 0 ? rowbias_group : 1};
+  if (x2 == nullptr && rowbias == nullptr) choose_splits(M, N, K1, &p.splits, &p.kchunk);
+  if (p.splits > 1) {
+    const size_t need = (size_t)p.splits * M * N * sizeof(float);
+    if (workspace == nullptr || workspace_bytes < need) {  // fall back to no split rather than fail
+      p.splits = 1;
+      p.kchunk = K1;
+    } else {
+      p.ws = workspace;
+    }
+  }
+  const bool vec = ptr_aligned16(x1) && ptr_aligned16(W) && (ldx1 % 4 == 0) && (ldw % 4 == 0) && (K1 % 4 == 0) &&
+                   (x2 == nullptr || (ptr_aligned16(x2) && ldx2 % 4 == 0 && K2 % 4 == 0));
+  dim3 grid(ceil_div(N, TBN), ceil_div(M, TBM), p.splits);
+  if (vec)
+    linear_simt_kernel<true><<<grid, kTileThreads, 0, st>>>(p);
+  else
+    linear_simt_kernel<false><<<grid, kTileThreads, 0, st>>>(p);
+  FAR_CHECK_LAUNCH();
+  if (p.splits > 1) {
+    const long long tot = (long long)M * N;
+    splitk_reduce_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(p.ws, p.splits, bias, y, ldy, M, N, act,
+                                                                         act_cols);
+    FAR_CHECK_LAUNCH();
+  }
+  return FAR_OK;
+}
+
+}  // namespace far
+
+using namespace far;
+
+extern "C" int far_abi_version(void) { return 1; }
+
+extern "C" size_t far_linear_workspace_bytes(int M, int N, int K) {
+  int s, kc;
+  choose_splits(M, N, K, &s, &kc);
+  size_t b = (s > 1) ? (size_t)s * M * N * sizeof(float) : 0;
+  size_t tcb = tc_linear_workspace_bytes(M, N, K);
+  return (b > tcb ? b : tcb) + 256;
+}
+
+extern "C" int far_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W,
+                          int ldw, const float* bias, float* y, int ldy, int M, int N, int act, int act_cols,
+                          int engine, float* workspace, size_t workspace_bytes, void* stream) {
+  return linear_dispatch(x1, ldx1, K1, x2, ldx2, K2, W, ldw, bias, y, ldy, M, N, act, act_cols, engine, workspace,
+                         workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int far_layernorm_pre(const float* x, const float* pre_add, int pre_rows, const float* gamma,
+                                 const float* beta, const float* residual, float* y, int rows, int C, float eps,
+                                 void* stream) {
+  if (rows <= 0) return FAR_OK;
+  FAR_REQUIRE(x && gamma && beta && y && C > 0 && C <= 1024 && (pre_add == nullptr || pre_rows > 0));
+  const int wpb = 8;
+  layernorm_kernel<<<ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(x, pre_add, pre_rows, gamma, beta,
+                                                                               residual, y, rows, C, eps);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+extern "C" int far_layernorm(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
+                             int rows, int C, float eps, void* stream) {
+  if (rows <= 0) return FAR_OK;
+  FAR_REQUIRE(x && gamma && beta && y && C > 0 && C <= 1024);
+  const int wpb = 8;
+  layernorm_kernel<<<ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(x, nullptr, 1, gamma, beta, residual, y,
+                                                                               rows, C, eps);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+extern "C" int far_pos_encode_flatten(const float* feat, long long sn, long long sc, long long sh, long long sw,
+                                      const float* pe_hwc, float* out, int N, int C, int H, int W, void* stream) {
+  if (N <= 0) return FAR_OK;
+  FAR_REQUIRE(feat && pe_hwc && out && C > 0 && H > 0 && W > 0);
+  dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), N), block(32, 8);
+  pos_flatten_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(feat, sn, sc, sh, sw, pe_hwc, out, C, H, W);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+extern "C" int far_pose_blend_mp3d(const float* pred, const float* solver, int ld_solver, const float* wt,
+                                   const float* mean9, const float* std9, int scale_8pt, float* out, int B,
+                                   void* stream) {
+  if (B <= 0) return FAR_OK;
+  FAR_REQUIRE(pred && solver && wt && mean9 && std9 && out && ld_solver >= 9);
+  pose_blend_mp3d_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(pred, solver, ld_solver, wt, mean9, std9,
+                                                                            scale_8pt, out, B);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}

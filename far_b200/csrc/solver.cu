@@ -1,0 +1,441 @@
+// Weighted normalised 8-point + essential-matrix decomposition, no cuSOLVER.
+//   run_8point                  */third_party/prior_ransac/cv_geometry.py:772-833 (+ normalize_points :713-750,
+//                               normalize_transformation :753-769)
+//   decompose_essential_matrix  */third_party/prior_ransac/essential.py:99-139, motion_from_essential :41-64
+//   per-pair python loop        mp3d_loftr/src/loftr/utils/supervision.py:184-233 -> metrics.py:80-174
+//
+// Stage 1 (HBM-bound, one warp per pair): two coalesced passes over the pair's correspondences: means, then
+//   mean distance + the 45 unique entries of  A_c = sum_i w_i xc_i xc_i^T  on CENTRED coordinates, accumulated in
+//   fp64 registers.  The Hartley scale is applied afterwards as a diagonal congruence (A = D A_c D), which is
+//   exact algebra, so the reference's dense [N,N] diag_embed(w) (16.8 MB/pair at N=2048) never exists.
+// Stage 2 (one THREAD per pair, 32 pairs per warp in lock-step): register-resident cyclic Jacobi on the 9x9
+//   (fp32, like the reference's fp32 SVD), smallest eigenvector -> F_hat; rank-2 projection through the smallest
+//   right-singular vector of F_hat (3x3 Jacobi in fp64 on F^T F):  F_hat - (F_hat v3) v3^T  ==  U diag(s1,s2,0) V^T;
+//   de-normalise  T2^T F T1 ; divide by (F22 + 1e-8) when |F22| > 1e-8.
+#include "common.cuh"
+
+namespace far {
+
+// ------------------------------------------------------------------------------------------- Jacobi kernels
+template <typename T, int N>
+__device__ __forceinline__ void jacobi_eig(T (&A)[N][N], T (&V)[N][N], int max_sweeps, T tol) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) V[i][j] = (i == j) ? T(1) : T(0);
+#pragma unroll 1
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    T off = T(0), diag = T(0);
+#pragma unroll
+    for (int p = 0; p < N; ++p) {
+      diag += A[p][p] * A[p][p];
+#pragma unroll
+      for (int q = p + 1; q < N; ++q) off += A[p][q] * A[p][q];
+    }
+    if (off <= tol * tol * diag || off == T(0)) break;
+#pragma unroll
+    for (int p = 0; p < N - 1; ++p) {
+#pragma unroll
+      for (int q = p + 1; q < N; ++q) {
+        const T apq = A[p][q];
+        if (apq != T(0)) {
+          const T theta = (A[q][q] - A[p][p]) / (T(2) * apq);
+          const T t = (theta >= T(0) ? T(1) : T(-1)) / (fabs(theta) + sqrt(theta * theta + T(1)));
+          const T c = T(1) / sqrt(t * t + T(1));
+          const T s = t * c;
+          A[p][p] -= t * apq;
+          A[q][q] += t * apq;
+          A[p][q] = T(0);
+          A[q][p] = T(0);
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            if (k != p && k != q) {
+              const T akp = A[k][p], akq = A[k][q];
+              const T np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+              A[k][p] = np_; A[p][k] = np_;
+              A[k][q] = nq_; A[q][k] = nq_;
+            }
+            const T vkp = V[k][p], vkq = V[k][q];
+            V[k][p] = c * vkp - s * vkq;
+            V[k][q] = s * vkp + c * vkq;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Eigen-decomposition of the 3x3 symmetric M = F^T F (fp64).  Returns V columns sorted by DESCENDING eigenvalue.
+__device__ __forceinline__ void sym3_eig_sorted(const double (&M)[3][3], double (&V)[3][3], double (&lam)[3]) {
+  double A[3][3], W[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) A[i][j] = M[i][j];
+  jacobi_eig<double, 3>(A, W, 30, 1e-15);
+  double l0 = A[0][0], l1 = A[1][1], l2 = A[2][2];
+  int i0 = 0, i1 = 1, i2 = 2;
+  if (l0 < l1) { double tl = l0; l0 = l1; l1 = tl; int ti = i0; i0 = i1; i1 = ti; }
+  if (l1 < l2) { double tl = l1; l1 = l2; l2 = tl; int ti = i1; i1 = i2; i2 = ti; }
+  if (l0 < l1) { double tl = l0; l0 = l1; l1 = tl; int ti = i0; i0 = i1; i1 = ti; }
+  lam[0] = l0; lam[1] = l1; lam[2] = l2;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    V[k][0] = (i0 == 0) ? W[k][0] : (i0 == 1 ? W[k][1] : W[k][2]);
+    V[k][1] = (i1 == 0) ? W[k][0] : (i1 == 1 ? W[k][1] : W[k][2]);
+    V[k][2] = (i2 == 0) ? W[k][0] : (i2 == 1 ? W[k][1] : W[k][2]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- stage 1
+// per-pair record in the workspace: 45 doubles (upper triangle of A_c, row-major) + 6 doubles
+// (mu1x, mu1y, mu2x, mu2y, s1, s2) + count
+constexpr int kRec = 52;
+
+struct DensePts {  // far_eight_point: pts [P,N,2], weights [P,N] or NULL, counts [P] or NULL
+  const float* p1; const float* p2; const float* w; const int* counts; int N;
+  __device__ __forceinline__ int count(int pair) const { return counts ? min(counts[pair], N) : N; }
+  __device__ __forceinline__ void load(int pair, int i, float& x1, float& y1, float& x2, float& y2, float& wt) const {
+    const size_t o = (size_t)pair * N + i;
+    const float2 a = reinterpret_cast<const float2*>(p1)[o], b = reinterpret_cast<const float2*>(p2)[o];
+    x1 = a.x; y1 = a.y; x2 = b.x; y2 = b.y;
+    wt = w ? w[o] : 1.f;
+  }
+};
+struct RaggedPts {  // far_pose_from_matches: segment [off[b], off[b+1]) of pixel keypoints, K-normalised on the fly
+  const float* mk0; const float* mk1; const float* conf; const long long* off; const float* K0; const float* K1;
+  __device__ __forceinline__ int count(int pair) const { return (int)(off[pair + 1] - off[pair]); }
+  __device__ __forceinline__ void load(int pair, int i, float& x1, float& y1, float& x2, float& y2, float& wt) const {
+    const size_t o = (size_t)off[pair] + i;
+    const float2 a = reinterpret_cast<const float2*>(mk0)[o], b = reinterpret_cast<const float2*>(mk1)[o];
+    const float* k0 = K0 + (size_t)pair * 9;
+    const float* k1 = K1 + (size_t)pair * 9;
+    // (kpts - K[[0,1],[2,2]]) / K[[0,1],[0,1]]   (metrics.py:88-89)
+    x1 = (a.x - k0[2]) / k0[0]; y1 = (a.y - k0[5]) / k0[4];
+    x2 = (b.x - k1[2]) / k1[0]; y2 = (b.y - k1[5]) / k1[4];
+    wt = conf ? conf[o] : 1.f;
+  }
+};
+
+template <class Pts>
+__global__ void __launch_bounds__(128) eightpt_accumulate_kernel(Pts pts, int P, double* __restrict__ rec) {
+  const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (pair >= P) return;
+  const int n = pts.count(pair);
+  double* r = rec + (size_t)pair * kRec;
+  if (n < 8) {
+    if (lane == 0) r[51] = (double)n;
+    return;
+  }
+  // pass 1: means (normalize_points :736)
+  double sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0;
+  for (int i = lane; i < n; i += 32) {
+    float x1, y1, x2, y2, w;
+    pts.load(pair, i, x1, y1, x2, y2, w);
+    sx1 += x1; sy1 += y1; sx2 += x2; sy2 += y2;
+  }
+  const double m1x = warp_sum(sx1) / n, m1y = warp_sum(sy1) / n, m2x = warp_sum(sx2) / n, m2y = warp_sum(sy2) / n;
+  // pass 2: mean distance to the centroid (:738) + centred weighted moments
+  double d1 = 0, d2 = 0;
+  double a[45];
+#pragma unroll
+  for (int k = 0; k < 45; ++k) a[k] = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    float fx1, fy1, fx2, fy2, fw;
+    pts.load(pair, i, fx1, fy1, fx2, fy2, fw);
+    const double x1 = fx1 - m1x, y1 = fy1 - m1y, x2 = fx2 - m2x, y2 = fy2 - m2y, w = fw;
+    d1 += sqrt(x1 * x1 + y1 * y1);
+    d2 += sqrt(x2 * x2 + y2 * y2);
+    // X row = [x2*x1, x2*y1, x2, y2*x1, y2*y1, y2, x1, y1, 1]   (:810)
+    const double X[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1.0};
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < 9; ++p) {
+      const double wp = w * X[p];
+#pragma unroll
+      for (int q = p; q < 9; ++q) { a[k] = fma(wp, X[q], a[k]); ++k; }
+    }
+  }
+  d1 = warp_sum(d1) / n;
+  d2 = warp_sum(d2) / n;
+#pragma unroll
+  for (int k = 0; k < 45; ++k) a[k] = warp_sum(a[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 45; ++k) r[k] = a[k];
+    r[45] = m1x; r[46] = m1y; r[47] = m2x; r[48] = m2y;
+    r[49] = sqrt(2.0) / (d1 + 1e-8);  // scale (:739)
+    r[50] = sqrt(2.0) / (d2 + 1e-8);
+    r[51] = (double)n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- stage 2
+// F (row-major 3x3, fp32) for one pair from its record.  Returns false when the pair had < 8 points.
+__device__ __forceinline__ bool eightpt_solve(const double* __restrict__ r, float (&F)[9]) {
+  if (r[51] < 8.0) return false;
+  const double s1 = r[49], s2 = r[50];
+  // centred -> normalised: x~_n = D x~_c, D = diag(s2 s1, s2 s1, s2, s2 s1, s2 s1, s2, s1, s1, 1)
+  const double D[9] = {s2 * s1, s2 * s1, s2, s2 * s1, s2 * s1, s2, s1, s1, 1.0};
+  float A[9][9], V[9][9];
+  {
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < 9; ++p)
+#pragma unroll
+      for (int q = p; q < 9; ++q) {
+        const float v = (float)(r[k++] * D[p] * D[q]);
+        A[p][q] = v;
+        A[q][p] = v;
+      }
+  }
+  jacobi_eig<float, 9>(A, V, 10, 1e-8f);
+  // smallest eigenvalue's eigenvector == V[..., -1] of the SVD of the PSD matrix (:819-821)
+  int idx = 0;
+  float best = A[0][0];
+#pragma unroll
+  for (int c = 1; c < 9; ++c)
+    if (A[c][c] < best) { best = A[c][c]; idx = c; }
+  double Fh[3][3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    float v = V[k][0];
+#pragma unroll
+    for (int c = 1; c < 9; ++c) v = (idx == c) ? V[k][c] : v;
+    Fh[k / 3][k % 3] = (double)v;
+  }
+  // rank-2 projection (:824-827): F_hat - (F_hat v3) v3^T with v3 = right-singular vector of the smallest sigma
+  double M[3][3], Vs[3][3], lam[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) M[i][j] = Fh[0][i] * Fh[0][j] + Fh[1][i] * Fh[1][j] + Fh[2][i] * Fh[2][j];
+  sym3_eig_sorted(M, Vs, lam);
+  double Fp[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double fv = Fh[i][0] * Vs[0][2] + Fh[i][1] * Vs[1][2] + Fh[i][2] * Vs[2][2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Fp[i][j] = Fh[i][j] - fv * Vs[j][2];
+  }
+  // F = T2^T Fp T1, T = [[s,0,-s mx],[0,s,-s my],[0,0,1]]   (:828)
+  const double m1x = r[45], m1y = r[46], m2x = r[47], m2y = r[48];
+  const double T1[3][3] = {{s1, 0, -s1 * m1x}, {0, s1, -s1 * m1y}, {0, 0, 1}};
+  const double T2[3][3] = {{s2, 0, -s2 * m2x}, {0, s2, -s2 * m2y}, {0, 0, 1}};
+  double G[3][3], Fe[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) G[i][j] = Fp[i][0] * T1[0][j] + Fp[i][1] * T1[1][j] + Fp[i][2] * T1[2][j];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Fe[i][j] = T2[0][i] * G[0][j] + T2[1][i] * G[1][j] + T2[2][i] * G[2][j];
+  // normalize_transformation (:753-769): M / (M22 + eps) where |M22| > eps
+  const float f22 = (float)Fe[2][2];
+  const bool nz = fabsf(f22) > 1e-8f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float v = (float)Fe[k / 3][k % 3];
+    F[k] = nz ? v / (f22 + 1e-8f) : v;
+  }
+  return true;
+}
+
+// R1, R2 (row-major) and t from E (essential.py:99-139).  SVD via the eigen-decomposition of E^T E:
+// V sorted by descending sigma, u_i = E v_i / sigma_i (i = 1,2), u3 = u1 x u2  (=> det U = +1, the state the
+// reference reaches after its det(U) < 0 fix), v3 negated when det V < 0.
+__device__ __forceinline__ void essential_decompose(const float (&Ef)[9], float (&R1)[9], float (&R2)[9], float (&t)[3]) {
+  double E[3][3], M[3][3], V[3][3], lam[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) E[k / 3][k % 3] = (double)Ef[k];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) M[i][j] = E[0][i] * E[0][j] + E[1][i] * E[1][j] + E[2][i] * E[2][j];
+  sym3_eig_sorted(M, V, lam);
+  double U[3][3];
+  // u1
+  double n1 = 0, u1[3], u2[3], u3[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { u1[i] = E[i][0] * V[0][0] + E[i][1] * V[1][0] + E[i][2] * V[2][0]; n1 += u1[i] * u1[i]; }
+  n1 = sqrt(n1);
+  if (n1 > 1e-300) { u1[0] /= n1; u1[1] /= n1; u1[2] /= n1; } else { u1[0] = 1; u1[1] = 0; u1[2] = 0; }
+  double n2 = 0, dp = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) u2[i] = E[i][0] * V[0][1] + E[i][1] * V[1][1] + E[i][2] * V[2][1];
+  dp = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { u2[i] -= dp * u1[i]; n2 += u2[i] * u2[i]; }
+  n2 = sqrt(n2);
+  if (n2 > 1e-300) { u2[0] /= n2; u2[1] /= n2; u2[2] /= n2; }
+  else {  // rank <= 1: any unit vector orthogonal to u1
+    const double ex = fabs(u1[0]) < 0.9 ? 1.0 : 0.0, ey = 1.0 - ex;
+    const double d = ex * u1[0] + ey * u1[1];
+    u2[0] = ex - d * u1[0]; u2[1] = ey - d * u1[1]; u2[2] = -d * u1[2];
+    const double nn = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+    u2[0] /= nn; u2[1] /= nn; u2[2] /= nn;
+  }
+  u3[0] = u1[1] * u2[2] - u1[2] * u2[1];
+  u3[1] = u1[2] * u2[0] - u1[0] * u2[2];
+  u3[2] = u1[0] * u2[1] - u1[1] * u2[0];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { U[i][0] = u1[i]; U[i][1] = u2[i]; U[i][2] = u3[i]; }
+  const double detV = V[0][0] * (V[1][1] * V[2][2] - V[1][2] * V[2][1]) - V[0][1] * (V[1][0] * V[2][2] - V[1][2] * V[2][0]) +
+                      V[0][2] * (V[1][0] * V[2][1] - V[1][1] * V[2][0]);
+  if (detV < 0) { V[0][2] = -V[0][2]; V[1][2] = -V[1][2]; V[2][2] = -V[2][2]; }
+  // R1 = U W V^T, R2 = U W^T V^T, W = [[0,-1,0],[1,0,0],[0,0,1]]:  U W = [u2, -u1, u3],  U W^T = [-u2, u1, u3]
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double a = U[i][1] * V[j][0] - U[i][0] * V[j][1];
+      const double c = U[i][2] * V[j][2];
+      R1[i * 3 + j] = (float)(a + c);
+      R2[i * 3 + j] = (float)(-a + c);
+    }
+  t[0] = (float)u3[0]; t[1] = (float)u3[1]; t[2] = (float)u3[2];
+}
+
+__global__ void __launch_bounds__(64) eightpt_solve_kernel(const double* __restrict__ rec, int P, float* __restrict__ Fout) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= P) return;
+  float F[9];
+  if (!eightpt_solve(rec + (size_t)pair * kRec, F)) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) F[k] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Fout[(size_t)pair * 9 + k] = F[k];
+}
+
+__global__ void __launch_bounds__(128) essential_decompose_kernel(const float* __restrict__ E, int P, float* __restrict__ R1,
+                                                                  float* __restrict__ R2, float* __restrict__ t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  float e[9], r1[9], r2[9], tt[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) e[k] = E[(size_t)i * 9 + k];
+  essential_decompose(e, r1, r2, tt);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { R1[(size_t)i * 9 + k] = r1[k]; R2[(size_t)i * 9 + k] = r2[k]; }
+  t[(size_t)i * 3 + 0] = tt[0]; t[(size_t)i * 3 + 1] = tt[1]; t[(size_t)i * 3 + 2] = tt[2];
+}
+
+// pose_from_matches stage 2: E + the 4 candidates into cand[pair][ 2*9 + 3 ] floats (R1, R2, t)
+__global__ void __launch_bounds__(64) pose_solve_kernel(const double* __restrict__ rec, int P, float* __restrict__ Eout,
+                                                        float* __restrict__ cand) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= P) return;
+  float F[9], r1[9], r2[9], tt[3];
+  if (!eightpt_solve(rec + (size_t)pair * kRec, F)) {
+    // < 8 matches: identity pose, E = I  (supervision.py:222-224 fallback)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { F[k] = (k % 4 == 0) ? 1.f : 0.f; r1[k] = F[k]; r2[k] = F[k]; }
+    tt[0] = tt[1] = tt[2] = 0.f;
+  } else {
+    essential_decompose(F, r1, r2, tt);
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    Eout[(size_t)pair * 9 + k] = F[k];
+    cand[(size_t)pair * 21 + k] = r1[k];
+    cand[(size_t)pair * 21 + 9 + k] = r2[k];
+  }
+  cand[(size_t)pair * 21 + 18] = tt[0]; cand[(size_t)pair * 21 + 19] = tt[1]; cand[(size_t)pair * 21 + 20] = tt[2];
+}
+
+// stage 3 (one warp per pair): cheirality votes of the 4 candidates (R1,t),(R1,-t),(R2,t),(R2,-t) -- the order of
+// motion_from_essential (essential.py:60-62) -- the first candidate with the most votes wins (metrics.py:165-170
+// keeps the first strictly-better recoverPose result).
+__global__ void __launch_bounds__(128) pose_select_kernel(RaggedPts pts, int P, const float* __restrict__ cand,
+                                                          float* __restrict__ Rt, int* __restrict__ npos) {
+  const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (pair >= P) return;
+  const int n = pts.count(pair);
+  const float* c = cand + (size_t)pair * 21;
+  int votes[4] = {0, 0, 0, 0};
+  if (n >= 8) {
+    for (int i = lane; i < n; i += 32) {
+      float x0, y0, x1, y1, w;
+      pts.load(pair, i, x0, y0, x1, y1, w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float* R = c + (k >> 1) * 9;
+        const float sg = (k & 1) ? -1.f : 1.f;
+        const float tx = sg * c[18], ty = sg * c[19], tz = sg * c[20];
+        const float rx = R[0] * x0 + R[1] * y0 + R[2], ry = R[3] * x0 + R[4] * y0 + R[5], rz = R[6] * x0 + R[7] * y0 + R[8];
+        // a = (R x0h) x x1h ; b = t x x1h ; z0 = -(a.b)/(a.a) ; X1 = z0 R x0h + t
+        const float ax = ry - rz * y1, ay = rz * x1 - rx, az = rx * y1 - ry * x1;
+        const float bx = ty - tz * y1, by = tz * x1 - tx, bz = tx * y1 - ty * x1;
+        const float z0 = -(ax * bx + ay * by + az * bz) / fmaxf(ax * ax + ay * ay + az * az, 1e-20f);
+        const float z1 = z0 * rz + tz;
+        votes[k] += (z0 > 0.f && z1 > 0.f) ? 1 : 0;
+      }
+    }
+  }
+  int best = -1, bk = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int v = warp_sum(votes[k]);
+    if (v > best) { best = v; bk = k; }
+  }
+  if (lane == 0) {
+    const float* R = c + (bk >> 1) * 9;
+    const float sg = (bk & 1) ? -1.f : 1.f;
+    float* o = Rt + (size_t)pair * 12;
+    for (int i = 0; i < 3; ++i) {
+      o[i * 4 + 0] = R[i * 3 + 0]; o[i * 4 + 1] = R[i * 3 + 1]; o[i * 4 + 2] = R[i * 3 + 2];
+      o[i * 4 + 3] = (n >= 8) ? sg * c[18 + i] : 0.f;
+    }
+    npos[pair] = (n >= 8) ? best : 0;
+  }
+}
+
+}  // namespace far
+
+using namespace far;
+
+extern "C" size_t far_eight_point_workspace_bytes(int P) { return (size_t)P * (kRec * 8 + 21 * 4) + 256; }
+
+extern "C" int far_eight_point(const float* pts1, const float* pts2, const float* weights, const int* counts, int P,
+                               int N, float* F, float* workspace, size_t workspace_bytes, void* stream) {
+  if (P <= 0) return FAR_OK;
+  FAR_REQUIRE(pts1 && pts2 && F && workspace && N > 0);
+  if (workspace_bytes < (size_t)P * kRec * 8) return FAR_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* rec = reinterpret_cast<double*>(workspace);
+  DensePts pts{pts1, pts2, weights, counts, N};
+  eightpt_accumulate_kernel<DensePts><<<ceil_div(P, 4), 128, 0, st>>>(pts, P, rec);
+  FAR_CHECK_LAUNCH();
+  eightpt_solve_kernel<<<ceil_div(P, 64), 64, 0, st>>>(rec, P, F);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+extern "C" int far_essential_decompose(const float* E, int P, float* R1, float* R2, float* t, void* stream) {
+  if (P <= 0) return FAR_OK;
+  FAR_REQUIRE(E && R1 && R2 && t);
+  essential_decompose_kernel<<<ceil_div(P, 128), 128, 0, (cudaStream_t)stream>>>(E, P, R1, R2, t);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+extern "C" int far_pose_from_matches(const float* mkpts0, const float* mkpts1, const float* mconf,
+                                     const long long* offsets, int N, const float* K0, const float* K1, float* E,
+                                     float* Rt, int* n_pos, float* workspace, size_t workspace_bytes, void* stream) {
+  if (N <= 0) return FAR_OK;
+  FAR_REQUIRE(offsets && K0 && K1 && E && Rt && n_pos && workspace);
+  if (workspace_bytes < (size_t)N * (kRec * 8 + 21 * 4)) return FAR_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* rec = reinterpret_cast<double*>(workspace);
+  float* cand = reinterpret_cast<float*>(rec + (size_t)N * kRec);
+  RaggedPts pts{mkpts0, mkpts1, mconf, offsets, K0, K1};
+  eightpt_accumulate_kernel<RaggedPts><<<ceil_div(N, 4), 128, 0, st>>>(pts, N, rec);
+  FAR_CHECK_LAUNCH();
+  pose_solve_kernel<<<ceil_div(N, 64), 64, 0, st>>>(rec, N, E, cand);
+  FAR_CHECK_LAUNCH();
+  pose_select_kernel<<<ceil_div(N, 4), 128, 0, st>>>(pts, N, cand, Rt, n_pos);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}

@@ -1,0 +1,271 @@
+"""Tensor-level wrappers over the C ABI (include/far_sm100.h).  Each function cites the reference op it replaces.
+
+All inputs must be CUDA tensors; outputs are freshly allocated CUDA tensors.  No torch compute happens here
+beyond allocation and (cheap) layout normalisation.
+"""
+import math
+from ctypes import byref
+
+import torch
+
+from . import _lib as L
+from ._lib import ptr, f32c, stream, check
+
+
+def _ws(nbytes, device):
+    return L.workspace.get(int(nbytes), device)
+
+
+def linear(x, weight, bias=None, act=L.ACT_NONE, act_cols=-1, x2=None, engine=L.ENGINE_AUTO, out=None):
+    """y = act([x | x2] @ weight.T + bias)  -- nn.Linear (transformer.py:23-38 etc.).  x: [..., K1], x2: [..., K2]."""
+    lib = L.load()
+    lead = x.shape[:-1]
+    K1 = x.shape[-1]
+    x_ = f32c(x).reshape(-1, K1)
+    M = x_.shape[0]
+    N, Kt = weight.shape
+    K2 = 0
+    x2_ = None
+    if x2 is not None:
+        K2 = x2.shape[-1]
+        x2_ = f32c(x2).reshape(-1, K2)
+    assert Kt == K1 + K2, (Kt, K1, K2)
+    w = f32c(weight)
+    b = f32c(bias) if bias is not None else None
+    y = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=x.device)
+    nws = lib.far_linear_workspace_bytes(M, N, K1)
+    ws = _ws(nws, x.device)
+    check(lib.far_linear(ptr(x_), K1, K1, ptr(x2_), K2 if x2_ is not None else 0, K2, ptr(w), Kt, ptr(b), ptr(y), N,
+                         M, N, act, act_cols, engine, ptr(ws), ws.numel(), stream()), "far_linear")
+    return y.reshape(*lead, N)
+
+
+def layernorm(x, gamma, beta, eps, residual=None, pre_add=None):
+    """nn.LayerNorm over the last dim (transformer.py:59,64-66): residual + LN(x + pre_add).  `pre_add` is a
+    [rows_p, C] table broadcast over x's rows modulo rows_p (CrossBlock.pos_embed, transformer.py:337)."""
+    lib = L.load()
+    C = x.shape[-1]
+    x_ = f32c(x).reshape(-1, C)
+    r_ = f32c(residual).reshape(-1, C) if residual is not None else None
+    p_ = f32c(pre_add).reshape(-1, C) if pre_add is not None else None
+    y = torch.empty_like(x_)
+    check(lib.far_layernorm_pre(ptr(x_), ptr(p_), p_.shape[0] if p_ is not None else 1, ptr(f32c(gamma)),
+                                ptr(f32c(beta)), ptr(r_), ptr(y), x_.shape[0], C, float(eps), stream()),
+          "far_layernorm_pre")
+    return y.reshape(x.shape)
+
+
+def pos_encode_flatten(feat, pe_hwc):
+    """PositionEncodingSine.forward + rearrange 'n c h w -> n (h w) c' (position_encoding.py:37-42, loftr.py:100-101).
+    feat may be NCHW-contiguous or channels_last; pe_hwc: [H*W, C]."""
+    lib = L.load()
+    if feat.dtype != torch.float32:
+        feat = feat.float()
+    n, c, h, w = feat.shape
+    sn, sc, sh, sw = feat.stride()
+    if not (sc == 1 or sw == 1):
+        feat = feat.contiguous()
+        sn, sc, sh, sw = feat.stride()
+    out = torch.empty((n, h * w, c), dtype=torch.float32, device=feat.device)
+    check(lib.far_pos_encode_flatten(ptr(feat), sn, sc, sh, sw, ptr(f32c(pe_hwc)), ptr(out), n, c, h, w, stream()),
+          "far_pos_encode_flatten")
+    return out
+
+
+def linear_attention(q, k, v, eps=1e-6, feature_map_applied=False):
+    """LinearAttention.forward (linear_attention.py:20-52).  q [N,L,H,D]; k,v [N,S,H,D] -> [N,L,H,D]."""
+    lib = L.load()
+    N, Lq, H, D = q.shape
+    S = k.shape[1]
+    q_, k_, v_ = f32c(q), f32c(k), f32c(v)
+    out = torch.empty_like(q_)
+    nws = lib.far_linear_attention_workspace_bytes(N, S, H, D)
+    ws = _ws(nws, q.device)
+    C = H * D
+    check(lib.far_linear_attention(ptr(q_), C, ptr(k_), C, ptr(v_), C, ptr(out), C, N, Lq, S, H, D, float(eps),
+                                   int(feature_map_applied), ptr(ws), ws.numel(), stream()), "far_linear_attention")
+    return out
+
+
+def loftr_encoder_layer(x, source, weights, nhead, engine=L.ENGINE_AUTO):
+    """LoFTREncoderLayer.forward (transformer.py:44-67), masks None.  `weights`: dict with the layer's tensors
+    q_proj,k_proj,v_proj,merge,mlp0,mlp2,norm1_w,norm1_b,norm2_w,norm2_b (CUDA fp32 contiguous)."""
+    lib = L.load()
+    N, Lq, C = x.shape
+    S = source.shape[1]
+    x_, s_ = f32c(x), f32c(source)
+    out = torch.empty_like(x_)
+    w = L.EncoderLayerWeights(*[ptr(weights[k]) for k in ("q_proj", "k_proj", "v_proj", "merge", "mlp0", "mlp2",
+                                                          "norm1_w", "norm1_b", "norm2_w", "norm2_b")])
+    nws = lib.far_loftr_encoder_layer_workspace_bytes(N, Lq, S, C, nhead)
+    ws = _ws(nws, x.device)
+    check(lib.far_loftr_encoder_layer(ptr(x_), ptr(s_), ptr(out), N, Lq, S, C, nhead, byref(w), engine, ptr(ws),
+                                      ws.numel(), stream()), "far_loftr_encoder_layer")
+    return out
+
+
+def dual_softmax_match(feat_c0, feat_c1, hw0_c, hw1_c, thr, border_rm, temperature, scale0, scale1,
+                       return_conf_matrix=False, engine=L.ENGINE_AUTO):
+    """CoarseMatching.forward + get_coarse_match (coarse_matching.py:86-265), dual-softmax, eval.
+    Returns dict(b_ids,i_ids,j_ids,mconf,mkpts0_c,mkpts1_c[,conf_matrix]).  One device->host sync for M, as in the
+    reference's torch.where (:193)."""
+    lib = L.load()
+    N, Lq, C = feat_c0.shape
+    S = feat_c1.shape[1]
+    f0, f1 = f32c(feat_c0), f32c(feat_c1)
+    dev = f0.device
+    nws = lib.far_dual_softmax_match_workspace_bytes(N, Lq, S)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev)  # private: must survive until _gather
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    conf = torch.empty((N, Lq, S), dtype=torch.float32, device=dev) if return_conf_matrix else None
+    check(lib.far_dual_softmax_match_select(ptr(f0), ptr(f1), N, Lq, S, C, float(temperature), float(thr),
+                                            int(border_rm), hw0_c[0], hw0_c[1], hw1_c[0], hw1_c[1], ptr(conf),
+                                            ptr(cnt), engine, ptr(ws), nws, stream()), "far_dual_softmax_match_select")
+    M = int(cnt.item())  # the reference's sync point
+    b_ids = torch.empty(M, dtype=torch.int64, device=dev)
+    i_ids = torch.empty(M, dtype=torch.int64, device=dev)
+    j_ids = torch.empty(M, dtype=torch.int64, device=dev)
+    mconf = torch.empty(M, dtype=torch.float32, device=dev)
+    mk0 = torch.empty((M, 2), dtype=torch.float32, device=dev)
+    mk1 = torch.empty((M, 2), dtype=torch.float32, device=dev)
+    check(lib.far_dual_softmax_match_gather(N, Lq, hw0_c[1], hw1_c[1], float(scale0), float(scale1), M, ptr(b_ids),
+                                            ptr(i_ids), ptr(j_ids), ptr(mconf), ptr(mk0), ptr(mk1), ptr(ws), nws,
+                                            stream()), "far_dual_softmax_match_gather")
+    out = {"b_ids": b_ids, "i_ids": i_ids, "j_ids": j_ids, "mconf": mconf, "mkpts0_c": mk0, "mkpts1_c": mk1}
+    if return_conf_matrix:
+        out["conf_matrix"] = conf
+    return out
+
+
+def fine_preprocess(feat_f0, feat_f1, feat_c0, feat_c1, b_ids, i_ids, j_ids, W, stride, w0c, w1c, down_w, down_b,
+                    merge_w, merge_b):
+    """FinePreprocess.forward (fine_preprocess.py:29-59) with fine_concat_coarse_feat.  feat_f*: [N,Cf,Hf,Wf]
+    (any of NCHW / channels_last), feat_c*: [N,L,Cc].  Returns two [M, W*W, Cf] tensors."""
+    lib = L.load()
+    dev = feat_f0.device
+    n, Cf, Hf, Wf = feat_f0.shape
+    M = int(b_ids.shape[0])
+    out0 = torch.empty((M, W * W, Cf), dtype=torch.float32, device=dev)
+    out1 = torch.empty((M, W * W, Cf), dtype=torch.float32, device=dev)
+    if M == 0:
+        return out0, out1
+    if feat_f0.dtype != torch.float32:
+        feat_f0, feat_f1 = feat_f0.float(), feat_f1.float()
+    if feat_f0.stride() != feat_f1.stride() or not (feat_f0.stride(1) == 1 or feat_f0.stride(3) == 1):
+        feat_f0, feat_f1 = feat_f0.contiguous(), feat_f1.contiguous()
+    sn, sc, sh, sw = feat_f0.stride()
+    c0, c1 = f32c(feat_c0), f32c(feat_c1)
+    Cc = c0.shape[-1]
+    nws = lib.far_fine_preprocess_workspace_bytes(M, W * W, Cf, Cc)
+    ws = _ws(nws, dev)
+    check(lib.far_fine_preprocess(ptr(feat_f0), ptr(feat_f1), sn, sc, sh, sw, Hf, Wf, Cf, ptr(c0), ptr(c1),
+                                  c0.shape[1], c1.shape[1], Cc, ptr(b_ids), ptr(i_ids), ptr(j_ids), M, W, stride,
+                                  w0c, w1c, ptr(f32c(down_w)), ptr(f32c(down_b)), ptr(f32c(merge_w)),
+                                  ptr(f32c(merge_b)), ptr(out0), ptr(out1), ptr(ws), ws.numel(), stream()),
+          "far_fine_preprocess")
+    return out0, out1
+
+
+def fine_match(feat_f0, feat_f1, mkpts1_c, offset_scale):
+    """FineMatching.forward + get_fine_match (fine_matching.py:15-76).  Returns expec_f [M,3], mkpts1_f [M,2]."""
+    lib = L.load()
+    M, WW, C = feat_f0.shape
+    dev = feat_f0.device
+    expec = torch.empty((M, 3), dtype=torch.float32, device=dev)
+    mk1f = torch.empty((M, 2), dtype=torch.float32, device=dev)
+    if M == 0:
+        return expec, mk1f
+    check(lib.far_fine_match(ptr(f32c(feat_f0)), ptr(f32c(feat_f1)), M, WW, C, ptr(f32c(mkpts1_c)),
+                             float(offset_scale), ptr(expec), ptr(mk1f), stream()), "far_fine_match")
+    return expec, mk1f
+
+
+def eight_point(points1, points2, weights=None, counts=None):
+    """run_8point (third_party/prior_ransac/cv_geometry.py:772-833).  points [P,N,2], weights [P,N] -> F [P,3,3]."""
+    lib = L.load()
+    P, N, _ = points1.shape
+    if N < 8:
+        raise AssertionError(points1.shape)  # the reference asserts N >= 8 (:787)
+    p1, p2 = f32c(points1), f32c(points2)
+    w = f32c(weights) if weights is not None else None
+    c = counts.to(torch.int32).contiguous() if counts is not None else None
+    F = torch.empty((P, 3, 3), dtype=torch.float32, device=p1.device)
+    nws = lib.far_eight_point_workspace_bytes(P)
+    ws = _ws(nws, p1.device)
+    check(lib.far_eight_point(ptr(p1), ptr(p2), ptr(w), ptr(c), P, N, ptr(F), ptr(ws), ws.numel(), stream()),
+          "far_eight_point")
+    return F
+
+
+def essential_decompose(E):
+    """decompose_essential_matrix (third_party/prior_ransac/essential.py:99-139): E [*,3,3] -> R1,R2 [*,3,3], t [*,3,1]."""
+    lib = L.load()
+    lead = E.shape[:-2]
+    e = f32c(E).reshape(-1, 3, 3)
+    P = e.shape[0]
+    R1 = torch.empty_like(e)
+    R2 = torch.empty_like(e)
+    t = torch.empty((P, 3), dtype=torch.float32, device=e.device)
+    check(lib.far_essential_decompose(ptr(e), P, ptr(R1), ptr(R2), ptr(t), stream()), "far_essential_decompose")
+    return R1.reshape(*lead, 3, 3), R2.reshape(*lead, 3, 3), t.reshape(*lead, 3, 1)
+
+
+def pose_from_matches(mkpts0, mkpts1, mconf, offsets, K0, K1):
+    """Ragged per-pair weighted 8-point + cheirality-selected (R,t) (spvs_RT loop, supervision.py:184-233).
+    offsets: int64 [N+1] segment boundaries (m_bids is sorted).  Returns E [N,3,3], Rt [N,3,4], n_pos [N] int32."""
+    lib = L.load()
+    N = offsets.shape[0] - 1
+    dev = offsets.device
+    E = torch.empty((N, 3, 3), dtype=torch.float32, device=dev)
+    Rt = torch.empty((N, 3, 4), dtype=torch.float32, device=dev)
+    npos = torch.empty(N, dtype=torch.int32, device=dev)
+    nws = lib.far_eight_point_workspace_bytes(N)
+    ws = _ws(nws, dev)
+    check(lib.far_pose_from_matches(ptr(f32c(mkpts0)), ptr(f32c(mkpts1)), ptr(f32c(mconf)), ptr(offsets), N,
+                                    ptr(f32c(K0)), ptr(f32c(K1)), ptr(E), ptr(Rt), ptr(npos), ptr(ws), ws.numel(),
+                                    stream()), "far_pose_from_matches")
+    return E, Rt, npos
+
+
+def emm_bilinear_attn(qkv1, qkv2, pos, num_heads, scale, engine=L.ENGINE_AUTO):
+    """CrossAttention core (transformer.py:275-292): qkv1,qkv2 [B,N,3*C] (output of the shared qkv Linear),
+    pos [1 or B, N, 6] -> fundamental_1, fundamental_2 [B,h,d+6,d+6]."""
+    lib = L.load()
+    B, N, C3 = qkv1.shape
+    C = C3 // 3
+    d = C // num_heads
+    q1, q2, p_ = f32c(qkv1), f32c(qkv2), f32c(pos)
+    dv = d + 6
+    F1 = torch.empty((B, num_heads, dv, dv), dtype=torch.float32, device=q1.device)
+    F2 = torch.empty_like(F1)
+    nws = lib.far_emm_bilinear_attn_workspace_bytes(B, N, num_heads, d)
+    ws = _ws(nws, q1.device)
+    check(lib.far_emm_bilinear_attn(ptr(q1), ptr(q2), ptr(p_), p_.shape[0], B, N, num_heads, d, float(scale), ptr(F1),
+                                    ptr(F2), engine, ptr(ws), ws.numel(), stream()), "far_emm_bilinear_attn")
+    return F1, F2
+
+
+def softmax_attention(qkv, num_heads, scale):
+    """timm Attention core (vision_transformer.py:250-257): qkv [B,N,3*C] -> [B,N,C]."""
+    lib = L.load()
+    B, N, C3 = qkv.shape
+    C = C3 // 3
+    d = C // num_heads
+    q = f32c(qkv)
+    out = torch.empty((B, N, C), dtype=torch.float32, device=q.device)
+    nws = lib.far_softmax_attention_workspace_bytes(B, N, num_heads, d)
+    ws = _ws(nws, q.device)
+    check(lib.far_softmax_attention(ptr(q), B, N, num_heads, d, float(scale), ptr(out), ptr(ws), ws.numel(), stream()),
+          "far_softmax_attention")
+    return out
+
+
+def pose_blend_mp3d(pred, solver, wt, mean9, std9, scale_8pt=True):
+    """Gated fusion epilogue of forward_emm (transformer.py:436-469)."""
+    lib = L.load()
+    B = pred.shape[0]
+    s = f32c(solver)
+    out = torch.empty((B, 9), dtype=torch.float32, device=pred.device)
+    check(lib.far_pose_blend_mp3d(ptr(f32c(pred)), ptr(s), s.shape[1], ptr(f32c(wt)), ptr(f32c(mean9)),
+                                  ptr(f32c(std9)), int(scale_8pt), ptr(out), B, stream()), "far_pose_blend_mp3d")
+    return out

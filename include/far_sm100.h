@@ -1,0 +1,182 @@
+/* libfar_sm100.so -- C ABI of the B200-native FAR per-pair pose hot path.
+ *
+ * The reference (crockwell/far) is pure Python/PyTorch and has no FFI layer: its "plugin interface" for
+ * this path is a set of nn.Module.forward() methods.  Each entry point below replaces the op
+ * sequence of one of those methods; the comment on each cites the reference file:line it replaces
+ * (paths relative to /root/reference).  The Python host side (far_b200/) keeps the reference's module /
+ * parameter names and forward signatures and binds these symbols with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions: plain pointers + sizes, no torch types.  All tensors are fp32, row-major, device memory,
+ * 16-byte aligned unless stated; index tensors are int64 (what torch.where yields).  `stream` is a
+ * cudaStream_t passed as void*.  Functions never allocate and never synchronise; scratch memory comes from
+ * the caller (`*_workspace_bytes` says how much).  Return: FAR_OK or an FAR_ERR_* code (never throws).
+ */
+#ifndef FAR_SM100_H_
+#define FAR_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FAR_OK 0
+#define FAR_ERR_ARG 1       /* shape / alignment / null-pointer precondition violated */
+#define FAR_ERR_CUDA 2      /* a kernel launch failed (cudaGetLastError) */
+#define FAR_ERR_WORKSPACE 3 /* workspace too small */
+
+#define FAR_ACT_NONE 0
+#define FAR_ACT_RELU 1    /* nn.ReLU */
+#define FAR_ACT_GELU 2    /* nn.GELU (exact erf) */
+#define FAR_ACT_ELU1 3    /* F.elu(x) + 1  (linear_attention.py:10-11) */
+#define FAR_ACT_SIGMOID 4 /* nn.Sigmoid */
+
+/* ABI version of this header (bumped on any signature change). */
+int far_abi_version(void);
+
+/* ---- nn.Linear family --------------------------------------------------------------------------------
+ * y[M,N] = act( [x1 | x2] * W^T + bias ),  x1:[M,K1] (ld ldx1), x2:[M,K2] (ld ldx2, may be NULL with K2=0),
+ * W:[N,K1+K2] (ld ldw), bias:[N] or NULL, act applied to columns < act_cols only (act_cols<0: all).
+ * Replaces every nn.Linear on the path, e.g. q/k/v/merge/mlp of LoFTREncoderLayer
+ * (mp3d_loftr/src/loftr/loftr_module/transformer.py:23-38,55-63; the [x|message] concat of :63 is the
+ * x1|x2 pair), FinePreprocess.down_proj/merge_feat (fine_preprocess.py:19-20), CrossAttention.qkv /
+ * proj_fundamental (transformer.py:261-263), Mlp.fc1/fc2 (vit_layers/mlp.py:16-18), the FAR MLP heads
+ * (transformer.py:385-405; interiornetStreetlearn_8ptVit/src/model.py:94-108;
+ * mapfree_6dreg/lib/models/regression/model.py:66-84).
+ * `engine`: 0 = auto, 1 = fp32 CUDA-core tile engine, 2 = tcgen05 3xTF32 (TMA-fed; needs K%32==0,
+ * contiguous x1 (x2 NULL) and W).  Split-K is chosen internally when M is small and K large. */
+size_t far_linear_workspace_bytes(int M, int N, int K);
+int far_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
+               const float* bias, float* y, int ldy, int M, int N, int act, int act_cols, int engine,
+               float* workspace, size_t workspace_bytes, void* stream);
+
+/* y[r,:] = (residual ? residual[r,:] : 0) + LayerNorm(x[r,:]) * gamma + beta ; C <= 1024.
+ * Replaces nn.LayerNorm + the `x + message` residual (transformer.py:59,64-66; CrossBlock norms :339-347). */
+int far_layernorm(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
+                  int rows, int C, float eps, void* stream);
+/* Same with a broadcast pre-add: LayerNorm(x[r,:] + pre_add[r % pre_rows, :]) -- CrossBlock's
+ * `x = x + self.pos_embed` followed by norm1 (transformer.py:337,343); pre_add may be NULL. */
+int far_layernorm_pre(const float* x, const float* pre_add, int pre_rows, const float* gamma, const float* beta,
+                      const float* residual, float* y, int rows, int C, float eps, void* stream);
+
+/* out[n, h*W+w, c] = feat[n,c,h,w] + pe[c,h,w]  (PositionEncodingSine.forward + rearrange
+ * 'n c h w -> n (h w) c': mp3d_loftr/src/loftr/utils/position_encoding.py:37-42, loftr.py:100-101).
+ * feat given with element strides (sn, sc, sh, sw) so NCHW and channels_last both work;
+ * pe_hwc is the sine table laid out [H*W, C]. */
+int far_pos_encode_flatten(const float* feat, long long sn, long long sc, long long sh, long long sw,
+                           const float* pe_hwc, float* out, int N, int C, int H, int W, void* stream);
+
+/* ---- LinearAttention.forward (mp3d_loftr/src/loftr/loftr_module/linear_attention.py:20-52) -----------
+ * q:[N,L,H*D], k,v:[N,S,H*D] (row strides ldq/ldk/ldv), out:[N,L,H*D] (ld ldo).
+ * feature_map_applied != 0 means q,k already hold elu(x)+1 (fused into the projection epilogue). */
+size_t far_linear_attention_workspace_bytes(int N, int S, int H, int D);
+int far_linear_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out,
+                         int ldo, int N, int L, int S, int H, int D, float eps, int feature_map_applied,
+                         float* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- LoFTREncoderLayer.forward (transformer.py:44-67), masks None ------------------------------------
+ * x:[N,L,C] source:[N,S,C] -> out:[N,L,C] (out may alias x: every read of x precedes the final write).
+ * Weights are the layer's own tensors: wq,wk,wv,wmerge [C,C]; wmlp0 [2C,2C]; wmlp2 [C,2C]; LayerNorm
+ * gamma/beta [C] x2.  Composition: (q|k|v projections with fused elu+1) -> far_linear_attention ->
+ * merge -> LN -> mlp.0([x|msg]) ReLU -> mlp.2 -> LN + residual. */
+typedef struct {
+  const float *wq, *wk, *wv, *wmerge, *wmlp0, *wmlp2;
+  const float *g1, *b1, *g2, *b2;
+} far_encoder_layer_weights;
+size_t far_loftr_encoder_layer_workspace_bytes(int N, int L, int S, int C, int nhead);
+int far_loftr_encoder_layer(const float* x, const float* source, float* out, int N, int L, int S, int C,
+                            int nhead, const far_encoder_layer_weights* w, int engine, float* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* ---- CoarseMatching.forward + get_coarse_match (mp3d_loftr/src/loftr/utils/coarse_matching.py:86-265),
+ * dual_softmax branch, eval, no padding masks.  Two calls because M is data dependent (the reference
+ * synchronises in torch.where, :193):
+ *   _select: sim = (f0/sqrt(C)).(f1/sqrt(C))^T / temperature; row/col log-sum-exp; conf = softmax(sim,1) *
+ *            softmax(sim,2); threshold (strict >), border_rm frame on both grids, mutual-nearest test; writes
+ *            per-row decisions into the workspace, the total count to *num_matches (device int64) and, when
+ *            conf_out != NULL, the dense conf matrix [N,L,S] (`data['conf_matrix']`, :144).
+ *   _gather: order-preserving compaction into b_ids,i_ids,j_ids (ascending (b,i)), mconf, mkpts0_c,
+ *            mkpts1_c = (id % w, id / w) * scale  (:246-254).  Caller sizes outputs from *num_matches. */
+size_t far_dual_softmax_match_workspace_bytes(int N, int L, int S);
+int far_dual_softmax_match_select(const float* feat0, const float* feat1, int N, int L, int S, int C,
+                                  float temperature, float thr, int border_rm, int h0c, int w0c, int h1c,
+                                  int w1c, float* conf_out, long long* num_matches, int engine,
+                                  float* workspace, size_t workspace_bytes, void* stream);
+int far_dual_softmax_match_gather(int N, int L, int w0c, int w1c, float scale0, float scale1,
+                                  long long num_matches, long long* b_ids, long long* i_ids, long long* j_ids,
+                                  float* mconf, float* mkpts0_c, float* mkpts1_c, const float* workspace,
+                                  size_t workspace_bytes, void* stream);
+
+/* ---- FinePreprocess.forward (mp3d_loftr/src/loftr/loftr_module/fine_preprocess.py:29-59) -------------
+ * Gathers the WxW (stride `stride`, padding W/2) windows of the fine maps at the M matches directly
+ * (no F.unfold materialisation), projects the matched coarse tokens with down_proj, and applies merge_feat
+ * to [window | coarse] -> out0,out1 [M, W*W, Cf].  feat_f* given with element strides (channels_last or
+ * NCHW).  feat_c*: [N, L, Cc] post-transformer coarse features. */
+size_t far_fine_preprocess_workspace_bytes(long long M, int WW, int Cf, int Cc);
+int far_fine_preprocess(const float* feat_f0, const float* feat_f1, long long sn, long long sc, long long sh,
+                        long long sw, int Hf, int Wf, int Cf, const float* feat_c0, const float* feat_c1, int L0,
+                        int L1, int Cc, const long long* b_ids, const long long* i_ids, const long long* j_ids,
+                        long long M, int W, int stride, int w0c, int w1c, const float* down_w,
+                        const float* down_b, const float* merge_w, const float* merge_b, float* out0, float* out1,
+                        float* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- FineMatching.forward + get_fine_match (mp3d_loftr/src/loftr/utils/fine_matching.py:15-76) -------
+ * One warp per match: centre-token correlation, softmax(./sqrt(C)) over the WW window, spatial expectation
+ * on the [-1,1] grid (kornia dsnt semantics), std; expec_f [M,3]; mkpts1_f = mkpts1_c + coords*offset_scale
+ * with offset_scale = (W//2) * (hw0_i/hw0_f)  (:71). */
+int far_fine_match(const float* feat_f0, const float* feat_f1, long long M, int WW, int C,
+                   const float* mkpts1_c, float offset_scale, float* expec_f, float* mkpts1_f, void* stream);
+
+/* ---- run_8point (third_party/prior_ransac/cv_geometry.py:772-833, incl. normalize_points :713-750 and
+ * normalize_transformation :753-769).  One warp per pair, register-resident 9x9 accumulation, cyclic-Jacobi
+ * eigen-decomposition and 3x3 SVD (no cuSOLVER).  pts1,pts2:[P,N,2]; weights:[P,N] or NULL;
+ * counts:[P] (int32) valid correspondences per pair or NULL (= N).  F:[P,3,3]. */
+size_t far_eight_point_workspace_bytes(int P);
+int far_eight_point(const float* pts1, const float* pts2, const float* weights, const int* counts, int P, int N,
+                    float* F, float* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- decompose_essential_matrix / motion_from_essential (third_party/prior_ransac/essential.py:41-139)
+ * E:[P,3,3] -> R1,R2:[P,3,3], t:[P,3].  One thread per matrix (3x3 Jacobi SVD in registers). */
+int far_essential_decompose(const float* E, int P, float* R1, float* R2, float* t, void* stream);
+
+/* ---- per-pair solver glue for ragged matches (replaces the python loop of spvs_RT,
+ * mp3d_loftr/src/loftr/utils/supervision.py:184-233 -> estimate_pose metrics.py:80-174, with the in-repo
+ * weighted 8-point as the model solver).  Matches of pair b are the contiguous
+ * segment [offsets[b], offsets[b+1]) of mkpts0/mkpts1/mconf (m_bids is sorted).  K0,K1:[N,3,3] fp32.
+ * Outputs per pair: E [3,3], Rt [3,4] (cheirality-selected candidate; identity if < 8 matches),
+ * n_pos [int32] = cheirality votes of the winner. */
+int far_pose_from_matches(const float* mkpts0, const float* mkpts1, const float* mconf,
+                          const long long* offsets, int N, const float* K0, const float* K1, float* E,
+                          float* Rt, int* n_pos, float* workspace /* far_eight_point_workspace_bytes(N) */,
+                          size_t workspace_bytes, void* stream);
+
+/* ---- CrossAttention.forward core (mp3d: transformer.py:266-303; 8pt-ViT: vision_transformer.py:177-208)
+ * qkv1,qkv2: [B,Ntok,3,h,d] (the output of the shared qkv Linear on the two images), pos: [Bpos,Ntok,6]
+ * (Bpos = 1 broadcasts).  Computes, per (b,head), for X in {1,2}:
+ *   S_X = q_other k_X^T * scale;  P_X = softmax(S_X,-1) * softmax(S_X,-2);  V'_X = [v_X | pos];
+ *   F_X = V'_X^T P_X V'_X   -> F1,F2 [B,h,d+6,d+6]
+ * Two passes over S (LSE pass, recompute pass); S and P are never written to HBM. */
+size_t far_emm_bilinear_attn_workspace_bytes(int B, int Ntok, int h, int d);
+int far_emm_bilinear_attn(const float* qkv1, const float* qkv2, const float* pos, int Bpos, int B, int Ntok,
+                          int h, int d, float scale, float* F1, float* F2, int engine, float* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* ---- timm-style softmax attention of the 8pt-ViT blocks (vision_transformer.py:236-262):
+ * qkv:[B,Ntok,3,h,d] -> out:[B,Ntok,h*d] = softmax(q k^T * scale) v, heads re-interleaved. */
+size_t far_softmax_attention_workspace_bytes(int B, int Ntok, int h, int d);
+int far_softmax_attention(const float* qkv, int B, int Ntok, int h, int d, float scale, float* out,
+                          float* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- FAR gated fusion epilogues -----------------------------------------------------------------------
+ * mp3d (forward_emm, transformer.py:427-473, use_simple_moe + use_2wt [+ scale_8pt]): per row b,
+ *   t_s = scale_8pt ? renorm(solver t to |regressed t| in un-normalised space, clamp 1e-3..100) : solver t
+ *   out[b] = [ w0*pred_t + (1-w0)*t_s | w1*pred_R6 + (1-w1)*solver_R6 ]
+ * pred:[B,9], solver:[B,ld_solver>=9] (normalised 9-D first), wt:[B,2], mean/std:[9]. */
+int far_pose_blend_mp3d(const float* pred, const float* solver, int ld_solver, const float* wt,
+                        const float* mean9, const float* std9, int scale_8pt, float* out, int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAR_SM100_H_ */

@@ -1,0 +1,362 @@
+"""GPU parity tests proper: every CUDA op, through the C ABI, against the CPU oracle (oracle/far_oracle.py) on the
+same seeded inputs, plus the committed golden fixtures produced by the unmodified reference.
+
+Tolerances (stated per SURVEY.md 8d): integer outputs (match indices) bit-exact as ordered lists; fp32 tensors
+within a few ulp-scale absolute errors of the CPU result (reduction order differs); R,t / F within 1e-4 Frobenius.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import far_oracle as O
+from far_b200 import ops, synth, solver as fsolver
+from far_b200._lib import ACT_NONE, ACT_RELU, ACT_GELU, ACT_ELU1, ACT_SIGMOID, ENGINE_SIMT
+from far_b200.loftr import (LoFTR, far_eval_cfg, LocalFeatureTransformer, CoarseMatching, FinePreprocess,
+                            FineMatching, PositionEncodingSine, LocalFeatureTransformerRegressor)
+from tests.helpers import assert_close, f_normalize, pose_set_distance, maxdiff
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------- linear family
+@pytest.mark.parametrize("M,N,K", [(300, 256, 256), (1, 9, 512), (77, 130, 280), (4800, 512, 512), (33, 512, 35840)])
+@pytest.mark.parametrize("act", [ACT_NONE, ACT_RELU, ACT_GELU, ACT_ELU1, ACT_SIGMOID])
+def test_linear(M, N, K, act):
+    g = O.rng(M * 7 + N)
+    x, w, b = O.randn(g, M, K), O.randn(g, N, K, scale=K ** -0.5), O.randn(g, N, scale=0.1)
+    y = ops.linear(cu(x), cu(w), cu(b), act, engine=ENGINE_SIMT)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    ref = {ACT_NONE: lambda v: v, ACT_RELU: torch.relu, ACT_GELU: torch.nn.functional.gelu,
+           ACT_ELU1: lambda v: torch.nn.functional.elu(v) + 1, ACT_SIGMOID: torch.sigmoid}[act](ref)
+    assert_close(y, ref, 2e-5, 1e-5, f"linear {M}x{N}x{K} act{act}")
+
+
+def test_linear_two_segments_and_tail():
+    """[x1 | x2] K-segments (mlp.0 on cat[x, message]) and an unaligned tail (moe_predictor: 35840 + 22)."""
+    g = O.rng(3)
+    x1, x2 = O.randn(g, 50, 256), O.randn(g, 50, 22)
+    w, b = O.randn(g, 64, 278, scale=0.06), O.randn(g, 64)
+    y = ops.linear(cu(x1), cu(w), cu(b), ACT_RELU, x2=cu(x2))
+    ref = torch.relu(torch.nn.functional.linear(torch.cat([x1, x2], -1).double(), w.double(), b.double()))
+    assert_close(y, ref, 2e-5, 1e-5, "two-segment linear")
+
+
+def test_layernorm_variants():
+    g = O.rng(4)
+    x, gm, bt, res, pre = O.randn(g, 333, 256), O.randn(g, 256), O.randn(g, 256), O.randn(g, 333, 256), O.randn(g, 111, 256)
+    y = ops.layernorm(cu(x), cu(gm), cu(bt), 1e-5, residual=cu(res))
+    assert_close(y, res + torch.nn.functional.layer_norm(x, (256,), gm, bt, 1e-5), 1e-5, 1e-5, "LN+res")
+    y = ops.layernorm(cu(x), cu(gm), cu(bt), 1e-6, pre_add=cu(pre))
+    assert_close(y, torch.nn.functional.layer_norm(x + pre.repeat(3, 1), (256,), gm, bt, 1e-6), 1e-5, 1e-5, "LN(pre)")
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_pos_encode_flatten(channels_last):
+    g = O.rng(5)
+    f = O.randn(g, 2, 256, 60, 80)
+    pe = PositionEncodingSine(256, temp_bug_fix=True).to(DEV)
+    fin = cu(f).contiguous(memory_format=torch.channels_last) if channels_last else cu(f)
+    assert_close(pe.forward_flatten(fin), O.add_pos_and_flatten(f, True), 1e-6, 0, "pos-enc flatten")
+    pe2 = PositionEncodingSine(256, temp_bug_fix=False).to(DEV)
+    assert_close(pe2.forward_flatten(fin), O.add_pos_and_flatten(f, False), 1e-6, 0, "pos-enc (buggy variant)")
+
+
+# ------------------------------------------------------------------------------------------- linear attention / K1
+@pytest.mark.parametrize("N,L,S,H,D", [(2, 300, 280, 8, 32), (1, 4800, 4800, 8, 32), (37, 25, 25, 8, 16), (3, 70, 90, 8, 16)])
+def test_linear_attention(N, L, S, H, D):
+    g = O.rng(L + S)
+    q, k, v = O.randn(g, N, L, H, D), O.randn(g, N, S, H, D), O.randn(g, N, S, H, D)
+    out = ops.linear_attention(cu(q), cu(k), cu(v))
+    assert_close(out, O.linear_attention(q.double(), k.double(), v.double()), 2e-5, 2e-5, "linear attention")
+
+
+def _load(module, prefix_sd):
+    module.load_state_dict({k: v.clone() for k, v in prefix_sd.items()}, strict=True)
+    return module.to(DEV).eval()
+
+
+def test_local_feature_transformer_vs_oracle_and_golden(golden_dir):
+    cfg = far_eval_cfg(0.0)
+    lft = LocalFeatureTransformer({**cfg["coarse"], "layer_names": ["self", "cross"]})
+    sd = synth.synth_state_dict(lft.state_dict(), 1234)
+    _load(lft, sd)
+    g = O.rng(11)
+    f0, f1 = O.randn(g, 2, 300, 256), O.randn(g, 2, 280, 256)
+    with torch.no_grad():
+        a0, a1 = lft(cu(f0), cu(f1))
+        o0, o1 = O.local_feature_transformer(sd, f0, f1, ["self", "cross"], 8)
+    assert_close(a0, o0, 5e-5, 1e-5, "LFT feat0 vs oracle")
+    assert_close(a1, o1, 5e-5, 1e-5, "LFT feat1 vs oracle")
+    gold = np.load(os.path.join(golden_dir, "stages.npz"))
+    assert_close(a0[:, ::3, ::5], torch.from_numpy(gold["lft_out0"]), 5e-5, 1e-5, "LFT feat0 vs reference golden")
+    assert_close(a1[:, ::3, ::5], torch.from_numpy(gold["lft_out1"]), 5e-5, 1e-5, "LFT feat1 vs reference golden")
+
+
+def test_fine_level_transformer():
+    cfg = far_eval_cfg(0.0)
+    lft = LocalFeatureTransformer(cfg["fine"])
+    sd = synth.synth_state_dict(lft.state_dict(), 99)
+    _load(lft, sd)
+    g = O.rng(12)
+    f0, f1 = O.randn(g, 211, 25, 128), O.randn(g, 211, 25, 128)
+    with torch.no_grad():
+        a0, a1 = lft(cu(f0), cu(f1))
+        o0, o1 = O.local_feature_transformer(sd, f0, f1, cfg["fine"]["layer_names"], 8)
+    assert_close(a0, o0, 5e-5, 1e-5, "fine LFT feat0")
+    assert_close(a1, o1, 5e-5, 1e-5, "fine LFT feat1")
+
+
+# ------------------------------------------------------------------------------------------- K2 coarse matching
+def _match(c0, c1, hw0, hw1, thr, border, conf=False):
+    cm = CoarseMatching({**far_eval_cfg(thr)["match_coarse"], "border_rm": border, "materialize_conf_matrix": conf})
+    cm.eval()
+    d = {"hw0_i": (hw0[0] * 8, hw0[1] * 8), "hw1_i": (hw1[0] * 8, hw1[1] * 8), "hw0_c": hw0, "hw1_c": hw1}
+    cm(cu(c0), cu(c1), d)
+    return d
+
+
+def _same_ids(d, o):
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(d[k].cpu(), o[k]), f"{k}: CUDA {d[k].numel()} vs oracle {o[k].numel()} matches"
+
+
+@pytest.mark.parametrize("thr,border", [(0.0, 2), (0.0, 0), (0.2, 2), (0.01, 1)])
+def test_coarse_matching_small_grid(thr, border, golden_dir):
+    g = O.rng(11)
+    O.randn(g, 2, 300, 256), O.randn(g, 2, 280, 256)  # keep the stream aligned with make_golden.gen_stages
+    c0, c1 = O.randn(g, 3, 12 * 16, 256, scale=4.0), O.randn(g, 3, 10 * 14, 256, scale=4.0)
+    d = _match(c0, c1, (12, 16), (10, 14), thr, border, conf=True)
+    o = O.coarse_matching(c0, c1, (12, 16), (10, 14), thr, border, 0.1, 8.0)
+    _same_ids(d, o)
+    assert_close(d["mconf"], o["mconf"], 1e-6, 1e-5, "mconf")
+    assert_close(d["mkpts0_c"], o["mkpts0_c"], 0, 0, "mkpts0_c")
+    assert_close(d["mkpts1_c"], o["mkpts1_c"], 0, 0, "mkpts1_c")
+    assert_close(d["conf_matrix"], o["conf_matrix"], 1e-7, 2e-5, "conf_matrix")
+    if thr == 0.0 and border == 2:
+        gold = np.load(os.path.join(golden_dir, "stages.npz"))
+        assert np.array_equal(d["b_ids"].cpu().numpy(), gold["cm_b"]) and np.array_equal(d["i_ids"].cpu().numpy(), gold["cm_i"]) \
+            and np.array_equal(d["j_ids"].cpu().numpy(), gold["cm_j"]), "match indices vs reference golden"
+
+
+def test_coarse_matching_full_grid_and_empty():
+    g = O.rng(21)
+    c0, c1 = O.randn(g, 1, 4800, 256, scale=3.0), O.randn(g, 1, 4800, 256, scale=3.0)
+    d = _match(c0, c1, (60, 80), (60, 80), 0.0, 2)
+    o = O.coarse_matching(c0, c1, (60, 80), (60, 80), 0.0, 2, 0.1, 8.0)
+    _same_ids(d, o)
+    assert d["conf_matrix"] is None
+    # genuine M == 0 path: threshold above every confidence
+    d0 = _match(c0, c1, (60, 80), (60, 80), 0.999, 2)
+    assert d0["b_ids"].numel() == 0 and d0["mkpts0_c"].shape == (0, 2)
+
+
+# ------------------------------------------------------------------------------------------- K3/K4 fine level
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_fine_preprocess_and_match(channels_last):
+    cfg = far_eval_cfg(0.0)
+    g = O.rng(13)
+    c0, c1 = O.randn(g, 3, 12 * 16, 256, scale=4.0), O.randn(g, 3, 12 * 16, 256, scale=4.0)
+    fp = FinePreprocess(cfg)
+    sdf = synth.synth_state_dict(fp.state_dict(), 1234)
+    _load(fp, sdf)
+    ff0, ff1 = O.randn(g, 3, 128, 48, 64), O.randn(g, 3, 128, 48, 64)
+    o = O.coarse_matching(c0, c1, (12, 16), (12, 16), 0.0, 0, 0.1, 8.0)  # border 0: windows hit the zero padding
+    d = {"hw0_c": (12, 16), "hw1_c": (12, 16), "hw0_f": (48, 64), "hw1_f": (48, 64), "hw0_i": (96, 128),
+         "b_ids": cu(o["b_ids"]), "i_ids": cu(o["i_ids"]), "j_ids": cu(o["j_ids"]),
+         "mkpts0_c": cu(o["mkpts0_c"]), "mkpts1_c": cu(o["mkpts1_c"])}
+    a, b = cu(ff0), cu(ff1)
+    if channels_last:
+        a, b = a.contiguous(memory_format=torch.channels_last), b.contiguous(memory_format=torch.channels_last)
+    u0, u1 = fp(a, b, cu(c0), cu(c1), d)
+    q0, q1 = O.fine_preprocess(sdf, ff0, ff1, c0, c1, o["b_ids"], o["i_ids"], o["j_ids"], 5, 4)
+    assert q0.shape[0] > 20
+    assert_close(u0, q0, 2e-5, 1e-5, "fine_preprocess feat0")
+    assert_close(u1, q1, 2e-5, 1e-5, "fine_preprocess feat1")
+    fm = FineMatching(cfg)
+    fm(u0, u1, d)
+    e, m0, m1 = O.fine_matching(q0, q1, o["mkpts0_c"], o["mkpts1_c"], 2.0)
+    assert_close(d["expec_f"], e, 2e-5, 0, "expec_f")
+    assert_close(d["mkpts1_f"], m1, 1e-4, 0, "mkpts1_f")  # 1e-4 px on coordinates up to ~640 (fp32 ulp there is 6e-5)
+    assert torch.equal(d["mkpts0_f"].cpu(), o["mkpts0_c"])
+
+
+def test_fine_empty():
+    cfg = far_eval_cfg(0.0)
+    fp = FinePreprocess(cfg).to(DEV)
+    e = torch.empty(0, dtype=torch.int64, device=DEV)
+    d = {"hw0_c": (12, 16), "hw1_c": (12, 16), "hw0_f": (48, 64), "hw0_i": (96, 128), "b_ids": e, "i_ids": e, "j_ids": e,
+         "mkpts0_c": torch.empty(0, 2, device=DEV), "mkpts1_c": torch.empty(0, 2, device=DEV)}
+    u0, u1 = fp(torch.zeros(1, 128, 48, 64, device=DEV), torch.zeros(1, 128, 48, 64, device=DEV),
+                torch.zeros(1, 192, 256, device=DEV), torch.zeros(1, 192, 256, device=DEV), d)
+    assert u0.shape == (0, 25, 128)
+    FineMatching(cfg)(u0, u1, d)
+    assert d["expec_f"].shape == (0, 3) and d["mkpts1_f"].shape == (0, 2)
+
+
+# ------------------------------------------------------------------------------------------- K7/K8 solver
+def test_eight_point_vs_oracle_and_golden(golden_dir):
+    p1, p2, w, Rg, tg = synth.two_view_geometry(16, 256, seed=5)
+    gold = np.load(os.path.join(golden_dir, "solver.npz"))
+    for weights, key in ((w, "F_w"), (None, "F_u")):
+        F = fsolver.run_8point(cu(p1), cu(p2), cu(weights) if weights is not None else None)
+        Fo = O.run_8point(p1.double(), p2.double(), weights.double() if weights is not None else None)
+        d = (f_normalize(F) - f_normalize(Fo)).flatten(1).norm(dim=1)
+        assert d.max() < 1e-4, f"{key}: Frobenius distance to fp64 oracle {d.max():.3e}"
+        dg = (f_normalize(F) - f_normalize(torch.from_numpy(gold[key]))).flatten(1).norm(dim=1)
+        assert dg.max() < 1e-3, f"{key}: Frobenius distance to reference fp32 golden {dg.max():.3e}"
+        # the reference's own scale convention: F22 == 1 wherever |F22| > 1e-8
+        assert_close(F[:, 2, 2], torch.ones(16), 1e-5, 0, "F22 normalisation")
+
+
+def test_eight_point_properties_large():
+    """Config-5 size (subset): P=512 x N=2048; epipolar residual of inliers, rank 2, recovers the true E."""
+    P, N = 512, 2048
+    p1, p2, w, Rg, tg = synth.two_view_geometry(P, N, seed=9, noise=1e-4, outlier_frac=0.0)
+    F = fsolver.run_8point(cu(p1), cu(p2), cu(w)).double().cpu()
+    sv = torch.linalg.svdvals(F)
+    assert (sv[:, 2] / sv[:, 0]).max() < 1e-5, "rank-2 enforcement"
+    tx = torch.zeros(P, 3, 3, dtype=torch.float64)
+    t = tg.double()
+    tx[:, 0, 1], tx[:, 0, 2], tx[:, 1, 0], tx[:, 1, 2], tx[:, 2, 0], tx[:, 2, 1] = -t[:, 2], t[:, 1], t[:, 2], -t[:, 0], -t[:, 1], t[:, 0]
+    Et = tx @ Rg.double()
+    d = (f_normalize(F) - f_normalize(Et)).flatten(1).norm(dim=1)
+    assert d.median() < 5e-3 and d.max() < 0.1, (d.median(), d.max())
+
+
+def test_essential_decompose(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "solver.npz"))
+    E = torch.from_numpy(gold["F_w"])
+    R1, R2, t = fsolver.decompose_essential_matrix(cu(E))
+    dR, dt = pose_set_distance(R1, R2, t, torch.from_numpy(gold["R1"]), torch.from_numpy(gold["R2"]), torch.from_numpy(gold["t"]))
+    assert dR.max() < 1e-4 and dt.max() < 1e-4, (dR.max(), dt.max())
+    for R in (R1, R2):
+        Rd = R.double().cpu()
+        assert_close(Rd @ Rd.transpose(1, 2), torch.eye(3).expand(16, 3, 3), 1e-5, 0, "orthonormal")
+        assert_close(torch.det(Rd), torch.ones(16), 1e-5, 0, "det +1")
+    Rs, ts = fsolver.motion_from_essential(cu(E))
+    assert Rs.shape == (16, 4, 3, 3) and ts.shape == (16, 4, 3, 1)
+
+
+def test_pose_from_matches_ragged():
+    """Ragged segments incl. an empty pair and a pair with < 8 matches (identity fallback, supervision.py:222-224)."""
+    K = synth.mp3d_intrinsics(4)
+    sizes = [300, 0, 5, 1000]
+    mk0, mk1, cf, Rs, ts = [], [], [], [], []
+    for b, n in enumerate(sizes):
+        p1, p2, w, Rg, tg = synth.two_view_geometry(1, max(n, 1), seed=30 + b, noise=1e-4, outlier_frac=0.0)
+        f, c = K[b, 0, 0], K[b, :2, 2]
+        mk0.append((p1[0] * f + c)[:n]); mk1.append((p2[0] * f + c)[:n]); cf.append(w[0, :n]); Rs.append(Rg[0]); ts.append(tg[0])
+    mk0, mk1, cf = torch.cat(mk0), torch.cat(mk1), torch.cat(cf)
+    data = {"m_bids": cu(torch.repeat_interleave(torch.arange(4), torch.tensor(sizes))), "mkpts0_f": cu(mk0),
+            "mkpts1_f": cu(mk1), "mconf": cu(cf)}
+    Rt = fsolver.estimate_pose_batched(data, cu(K), cu(K)).cpu()
+    off = np.cumsum([0] + sizes)
+    for b, n in enumerate(sizes):
+        Ro, to, Eo = O.pose_from_matches_8pt(mk0[off[b]:off[b + 1]], mk1[off[b]:off[b + 1]], cf[off[b]:off[b + 1]], K[b], K[b])
+        assert_close(Rt[b, :, :3], Ro, 2e-4, 0, f"pair {b} R vs oracle")
+        assert_close(Rt[b, :, 3], to, 2e-4, 0, f"pair {b} t vs oracle")
+        if n >= 8:  # and the true pose is recovered (t up to scale: unit vector)
+            assert_close(Rt[b, :, :3], Rs[b], 5e-3, 0, f"pair {b} R vs truth")
+            assert_close(Rt[b, :, 3], ts[b], 5e-3, 0, f"pair {b} t vs truth")
+    assert data["num_correspondences_before_ransac"].tolist() == sizes
+
+
+# ------------------------------------------------------------------------------------------- K5/K6 FAR head
+def test_far_head_vs_oracle_and_golden(golden_dir):
+    cfg = far_eval_cfg(0.0)
+    head = LocalFeatureTransformerRegressor(cfg)
+    sd = synth.synth_state_dict(head.state_dict(), 1234)
+    _load(head, sd)
+    g = O.rng(41)
+    B = 2
+    f0, f1 = O.randn(g, B, 4800, 256), O.randn(g, B, 4800, 256)
+    _, _, _, Rg, tg = synth.two_view_geometry(B, 16, seed=77)
+    rt = torch.cat([Rg, tg[:, :, None]], dim=2).double()
+    lps, outs, wts = [], [], []
+    for b in range(B):
+        lp, ilp = O.preprocess_helper(rt[b], 412 + b, 1000 + b, 301, 57)
+        with torch.no_grad():
+            pose, wt = O.far_head_mp3d(sd, f0[b:b + 1], f1[b:b + 1], lp, ilp, cfg)
+        lps.append(lp); outs.append(pose); wts.append(wt)
+    with torch.no_grad():
+        pose_c, _, wt_c = head(cu(f0), cu(f1), loftr_preds=cu(torch.cat(lps)), inv_loftr_preds=None)
+    assert_close(pose_c, torch.cat(outs), 1e-4, 1e-4, "FAR head 9-D pose")
+    assert_close(wt_c, torch.cat(wts), 1e-4, 0, "gating weights")
+
+
+def test_emm_bilinear_attn_small():
+    """CrossAttention core at the 8pt-ViT size (N=576, 3 heads x 64) vs the oracle's dense formula."""
+    g = O.rng(51)
+    B, N, h, d = 2, 576, 3, 64
+    C = h * d
+    p = {"qkv.weight": O.randn(g, 3 * C, C, scale=C ** -0.5), "qkv.bias": O.randn(g, 3 * C, scale=0.1),
+         "proj_fundamental.weight": torch.eye(C + 6 * h)[:C], "proj_fundamental.bias": torch.zeros(C)}
+    x1, x2, pos = O.randn(g, B, N, C), O.randn(g, B, N, C), O.rand(g, B, N, 6)
+    qkv1 = torch.nn.functional.linear(x1, p["qkv.weight"], p["qkv.bias"])
+    qkv2 = torch.nn.functional.linear(x2, p["qkv.weight"], p["qkv.bias"])
+    F1, F2 = ops.emm_bilinear_attn(cu(qkv1), cu(qkv2), cu(pos), h, d ** -0.5)
+
+    def dense(qa, kb, vb):
+        q = qa.reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)[0].double()
+        kk = kb.reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)[1].double()
+        v = vb.reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)[2].double()
+        s = (q @ kk.transpose(-2, -1)) * d ** -0.5
+        P = s.softmax(-1) * s.softmax(-2)
+        vp = torch.cat([v, pos.double().unsqueeze(1).repeat(1, h, 1, 1)], dim=3)
+        return (vp.transpose(-2, -1) @ P) @ vp
+
+    assert_close(F1, dense(qkv2, qkv1, qkv1), 1e-5, 1e-4, "fundamental_1")
+    assert_close(F2, dense(qkv1, qkv2, qkv2), 1e-5, 1e-4, "fundamental_2")
+
+
+def test_softmax_attention():
+    g = O.rng(52)
+    B, N, h, d = 3, 576, 3, 64
+    qkv = O.randn(g, B, N, 3 * h * d)
+    out = ops.softmax_attention(cu(qkv), h, d ** -0.5)
+    t = qkv.double().reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)
+    ref = (((t[0] @ t[1].transpose(-2, -1)) * d ** -0.5).softmax(-1) @ t[2]).transpose(1, 2).reshape(B, N, h * d)
+    assert_close(out, ref, 1e-5, 1e-4, "softmax attention")
+
+
+# ------------------------------------------------------------------------------------------- whole LoFTR.forward
+def test_loftr_forward_full_vs_reference_golden(golden_dir):
+    """One 640x480 pair through LoFTR.forward + forward_rt_prediction vs the fixture the unmodified reference
+    produced on CPU.  Bar: identical ordered match indices; near-tie flips are counted and reported."""
+    gold = np.load(os.path.join(golden_dir, "loftr_full.npz"))
+    cfg = far_eval_cfg(0.0)
+    model = LoFTR(cfg)
+    sd = synth.synth_state_dict(model.state_dict(), int(gold["seed"][0]))
+    _load(model, sd)
+    img0, img1 = synth.synth_pair_images(1, seed=int(gold["seed"][1]))
+    data = {"image0": cu(img0), "image1": cu(img1)}
+    with torch.no_grad():
+        model(data)
+    ids = np.stack([data[k].cpu().numpy() for k in ("b_ids", "i_ids", "j_ids")], 1)
+    gids = np.stack([gold[k] for k in ("b_ids", "i_ids", "j_ids")], 1).astype(np.int64)
+    a, b = {tuple(r) for r in ids.tolist()}, {tuple(r) for r in gids.tolist()}
+    lost, spurious = len(b - a), len(a - b)
+    print(f"matches CUDA {len(a)} / reference {len(b)}; lost {lost}, spurious {spurious}")
+    assert_close(data["featmap0"][0, ::53, ::7], torch.from_numpy(gold["featmap0_s"]), 2e-4, 1e-4, "featmap0")
+    assert_close(data["featmap1"][0, ::53, ::7], torch.from_numpy(gold["featmap1_s"]), 2e-4, 1e-4, "featmap1")
+    assert lost == 0 and spurious == 0, "match index set differs from the reference"
+    assert np.array_equal(ids, gids), "match order differs from the reference"
+    assert_close(data["mconf"], torch.from_numpy(gold["mconf"]), 1e-6, 1e-3, "mconf")
+    assert_close(data["mkpts1_f"], torch.from_numpy(gold["mkpts1_f"]), 2e-3, 0, "mkpts1_f (px)")
+    assert_close(data["expec_f"], torch.from_numpy(gold["expec_f"]), 1e-3, 0, "expec_f")
+    c = gold["counters"]
+    data.update({"loftr_rt": torch.from_numpy(gold["loftr_rt"]), "num_correspondences": torch.tensor([c[0]]),
+                 "num_correspondences_before_ransac": torch.tensor([c[1]]), "inliers_best_tight": torch.tensor([c[2]]),
+                 "inliers_best_ultra_tight": torch.tensor([c[3]])})
+    with torch.no_grad():
+        model.forward_rt_prediction(data)
+    assert_close(data["regressed_rt"], torch.from_numpy(gold["regressed_rt"]), 1e-4, 1e-4, "regressed_rt")
+    assert_close(data["gating_reg_weights"], torch.from_numpy(gold["gating"]), 1e-4, 0, "gating")
+    assert_close(torch.from_numpy(data["priorRT"]), torch.from_numpy(gold["priorRT"]), 1e-4, 0, "priorRT")
