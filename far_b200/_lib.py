@@ -30,6 +30,7 @@ class EncoderLayerWeights(Structure):
 _P = c_void_p
 _SIGS = {
     "far_abi_version": (c_int, []),
+    "far_launch_count": (ctypes.c_ulonglong, []),
     "far_linear_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "far_linear": (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int,
                            c_int, _P, c_size_t, _P]),

@@ -7,8 +7,11 @@
 
 #include "../../include/far_sm100.h"
 
+namespace far { extern unsigned long long g_launch_count; }
+
 #define FAR_CHECK_LAUNCH()                                                      \
   do {                                                                          \
+    ++::far::g_launch_count;                                                    \
     cudaError_t _e = cudaGetLastError();                                        \
     if (_e != cudaSuccess) {                                                    \
       fprintf(stderr, "[far_sm100] %s:%d launch failed: %s\n", __FILE__, __LINE__, \

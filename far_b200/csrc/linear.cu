@@ -278,7 +278,10 @@ int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int l
 
 using namespace far;
 
+namespace far { unsigned long long g_launch_count = 0; }
+
 extern "C" int far_abi_version(void) { return 1; }
+extern "C" unsigned long long far_launch_count(void) { return far::g_launch_count; }
 
 extern "C" size_t far_linear_workspace_bytes(int M, int N, int K) {
   int s, kc;

@@ -34,6 +34,8 @@ extern "C" {
 
 /* ABI version of this header (bumped on any signature change). */
 int far_abi_version(void);
+/* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+unsigned long long far_launch_count(void);
 
 /* ---- nn.Linear family --------------------------------------------------------------------------------
  * y[M,N] = act( [x1 | x2] * W^T + bias ),  x1:[M,K1] (ld ldx1), x2:[M,K2] (ld ldx2, may be NULL with K2=0),

@@ -153,7 +153,7 @@ def test_coarse_matching_full_grid_and_empty():
     _same_ids(d, o)
     assert d["conf_matrix"] is None
     # genuine M == 0 path: threshold above every confidence
-    d0 = _match(c0, c1, (60, 80), (60, 80), 0.999, 2)
+    d0 = _match(c0, c1, (60, 80), (60, 80), 1.0, 2)  # conf <= 1 always
     assert d0["b_ids"].numel() == 0 and d0["mkpts0_c"].shape == (0, 2)
 
 
