@@ -1,9 +1,363 @@
-// tcgen05 3xTF32 engine -- placeholder until the TMA/TMEM kernel lands (next milestone).
+// tcgen05 3xTF32 GEMM engine for sm_100a:  C[M,N] = act( A[M,K] * B[N,K]^T + bias ),  fp32 in / fp32 out.
+//
+// Why 3xTF32: every reference GEMM on the path is IEEE fp32 and "bit-exact match indices" needs ~fp32 accuracy;
+// tcgen05 has no fp32 MMA kind.  Each operand is split  x = hi + lo  (hi = x with the low 13 mantissa bits cleared,
+// lo = x - hi exactly) and the product is accumulated as  lo*hi + hi*lo + hi*hi  in the fp32 TMEM accumulator
+// (error ~2^-21 relative per product; SURVEY.md 7 measured an identical match set with this scheme).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0     TMA producer : cp.async.bulk.tensor (SWIZZLE_128B, 128-row x 32-float boxes) of Ahi,Alo,Bhi,Blo into
+//                             a 3-stage shared-memory ring, mbarrier complete_tx
+//   warp 1     MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M128 x N128 x K8), 12 per
+//                             stage, accumulating into one of two 128-column TMEM accumulators; tcgen05.commit
+//                             releases the smem stage / publishes the accumulator
+//   warps 2-5  epilogue     : tcgen05.ld (32 lanes x 32 columns per warp), bias + activation, vectorised global store;
+//                             overlaps the next tile's main loop through the second accumulator
+// The hi/lo split of both operands is a separate elementwise kernel into the caller's workspace (no in-kernel
+// conversion => the main loop is pure TMA -> UMMA).
+#include <cuda.h>
+
 #include "tc_gemm.cuh"
+
 namespace far {
-bool tc_linear_supported(const float*, int, int, const float*, int, int, const float*, int, int, int) { return false; }
-bool tc_engine_default_on() { return false; }
-size_t tc_linear_workspace_bytes(int, int, int) { return 0; }
-int tc_linear(const float*, int, int, const float*, int, int, const float*, int, const float*, float*, int, int, int,
-              int, int, float*, size_t, cudaStream_t) { return FAR_ERR_ARG; }
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;  // BK floats = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;                   // tf32: 32 bytes of K per MMA
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;     // 16 KiB per operand tile
+constexpr int STAGE_BYTES = 4 * TILE_BYTES; // Ahi, Alo, Bhi, Blo
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 2 * BN;           // two accumulators
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address >> 4 in [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B) >> 4
+// in [32,46), version = 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format TF32 (2) [7,10)/[10,13), K-major A and B,
+// N >> 3 in [17,23), M >> 4 in [24,29).
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct GemmArgs {
+  float* C; int ldc;
+  const float* bias;
+  int M, N, K;
+  int act, act_cols;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+               const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, GemmArgs p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + BM - 1) / BM;
+  const int num_tiles = tiles_m * tiles_n;
+  const int kblocks = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it at the end
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sbase = base + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sbase + 1 * TILE_BYTES, &mapAlo, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sbase + 2 * TILE_BYTES, &mapBhi, full_bar(stage), kb * BK, n0);
+          tma_load_2d(sbase + 3 * TILE_BYTES, &mapBlo, full_bar(stage), kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sbase = base + stage * STAGE_BYTES;
+          const uint64_t dAhi = make_kmajor_sw128_desc(sbase + 0 * TILE_BYTES);
+          const uint64_t dAlo = make_kmajor_sw128_desc(sbase + 1 * TILE_BYTES);
+          const uint64_t dBhi = make_kmajor_sw128_desc(sbase + 2 * TILE_BYTES);
+          const uint64_t dBlo = make_kmajor_sw128_desc(sbase + 3 * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128-byte swizzle row
+            umma_tf32(tmem_d, dAlo + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);  // small terms first
+            umma_tf32(tmem_d, dAhi + koff, dBlo + koff, kIdescTf32, 1u);
+            umma_tf32(tmem_d, dAhi + koff, dBhi + koff, kIdescTf32, 1u);
+          }
+          umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));      // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane window of this warp: lanes [32*quarter, 32*quarter + 32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int actc = p.act_cols < 0 ? p.N : p.act_cols;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        const int col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) {
+          float* dst = p.C + (size_t)row * p.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = col0 + j + e;
+              float t = __uint_as_float(v[j + e]);
+              if (col < p.N) {
+                if (p.bias) t += __ldg(p.bias + col);
+                if (col < actc) t = apply_act(t, p.act);
+              }
+              o[e] = t;
+            }
+            if (vec_ok && col0 + j + 3 < p.N) {
+              *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (col0 + j + e < p.N) dst[j + e] = o[e];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// x = hi + lo with hi = tf32-truncated x.  Handles the [x1 | x2] concatenation: dst row stride = K1 + K2.
+__global__ void split_tf32_kernel(const float* __restrict__ x1, int ld1, int K1, const float* __restrict__ x2, int ld2,
+                                  int K2, long long rows, float* __restrict__ hi, float* __restrict__ lo) {
+  const int K = K1 + K2;
+  const long long total = rows * K;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / K;
+    const int c = (int)(idx % K);
+    const float v = (c < K1) ? x1[r * ld1 + c] : x2[r * ld2 + (c - K1)];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[idx] = h;
+    lo[idx] = v - h;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, K] tensor, box = 128 rows x 32 floats, SWIZZLE_128B, zero fill out of bounds.
+static bool make_map(CUtensorMap* map, const float* ptr, long long rows, int K) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static inline size_t al(size_t v) { return (v + 1023) & ~size_t(1023); }
+
+}  // namespace tc
+
+bool tc_engine_default_on() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FAR_TC");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+bool tc_linear_supported(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
+                         int M, int N) {
+  (void)x1; (void)ldx1; (void)x2; (void)ldx2; (void)W;
+  const int K = K1 + K2;
+  if (K % 4 != 0 || K < 32 || ldw != K) return false;         // TMA: 16-byte row pitch; weights contiguous
+  if ((long long)M * N < 128LL * 128 * 32) return false;      // small problems: CUDA-core engine (split-K, HBM-bound)
+  return tc::get_encode() != nullptr;
+}
+
+size_t tc_linear_workspace_bytes(int M, int N, int K) {
+  return 2 * tc::al((size_t)M * K * 4) + 2 * tc::al((size_t)N * K * 4) + 2048;
+}
+
+int tc_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
+              const float* bias, float* y, int ldy, int M, int N, int act, int act_cols, float* workspace,
+              size_t workspace_bytes, cudaStream_t st) {
+  using namespace tc;
+  const int K = K1 + K2;
+  if (workspace == nullptr || workspace_bytes < tc_linear_workspace_bytes(M, N, K)) return FAR_ERR_WORKSPACE;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  float* xhi = reinterpret_cast<float*>(base);
+  float* xlo = reinterpret_cast<float*>(base + al((size_t)M * K * 4));
+  float* whi = reinterpret_cast<float*>(base + 2 * al((size_t)M * K * 4));
+  float* wlo = reinterpret_cast<float*>(base + 2 * al((size_t)M * K * 4) + al((size_t)N * K * 4));
+  const int sblocks = kNumSMs * 8;
+  split_tf32_kernel<<<sblocks, 256, 0, st>>>(x1, ldx1, K1, x2, ldx2, K2, M, xhi, xlo);
+  FAR_CHECK_LAUNCH();
+  split_tf32_kernel<<<sblocks, 256, 0, st>>>(W, ldw, K, nullptr, 0, 0, N, whi, wlo);
+  FAR_CHECK_LAUNCH();
+  CUtensorMap mAhi, mAlo, mBhi, mBlo;
+  if (!make_map(&mAhi, xhi, M, K) || !make_map(&mAlo, xlo, M, K) || !make_map(&mBhi, whi, N, K) ||
+      !make_map(&mBlo, wlo, N, K))
+    return FAR_ERR_CUDA;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    attr_set = true;
+  }
+  GemmArgs p{y, ldy, bias, M, N, K, act, act_cols};
+  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, p);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
 }  // namespace far

@@ -237,3 +237,27 @@ def load_prior_ransac():
             return ns
         finally:
             sys.path.remove(pr)
+
+
+def vit8pt_args():
+    """argparse.Namespace of the 8pt-ViT eval recipe (interiornetStreetlearn_8ptVit/scripts + train.py:403-445)."""
+    return types.SimpleNamespace(pool_size=60, fc_hidden_size=512, use_loftr_gating=True, use_normalized_6d=True,
+                                 fusion_transformer=True, transformer_depth=6,
+                                 T_pose=torch.tensor([[0., 0., 1.]]))
+
+
+def load_vit8pt():
+    """Reference ViTEss class (interiornetStreetlearn_8ptVit/src/model.py) with resnet18(pretrained=True) -> weights=None."""
+    with _subproject("interiornetStreetlearn_8ptVit"):
+        import torchvision.models as tvm
+        orig = tvm.resnet18
+        tvm.resnet18 = lambda pretrained=False, **kw: orig(weights=None)
+        try:
+            ns = types.SimpleNamespace()
+            mod = importlib.import_module("src.model")
+            ns.ViTEss = mod.ViTEss
+            ns.vt = importlib.import_module("src.modules.vision_transformer")
+            ns.resnet18_patch = (tvm, orig)
+            return ns
+        finally:
+            pass

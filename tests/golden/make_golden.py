@@ -161,14 +161,88 @@ def gen_solver():
     npz("solver.npz", F_w=F_w, F_u=F_u, R1=R1, R2=R2, t=t, R_gt=Rg, t_gt=tg, seed=np.array([5, 16, 256]))
 
 
+def gen_vit8pt():
+    """Reference ViTEss.forward (interiornetStreetlearn_8ptVit/src/model.py:165-217), B=2, 640x480 BGR 0-255."""
+    print("[vit8pt] reference ViTEss.forward, B=2")
+    ns = R.load_vit8pt()
+    mean = torch.tensor([0.1, -0.05, 0.2, 0.8, 0.02, -0.1, -0.02, 0.9, 0.05])
+    std = torch.tensor([0.9, 0.4, 0.8, 0.3, 0.2, 0.5, 0.2, 0.1, 0.15])
+    ref = ns.ViTEss(R.vit8pt_args(), mean, std).eval()
+    sd = synth.synth_state_dict(ref.state_dict(), SEED)
+    ref.load_state_dict(sd, strict=True)
+    g = np.random.default_rng(20240003)
+    B = 2
+    images = torch.from_numpy(g.integers(0, 256, size=(B, 2, 3, 480, 640)).astype(np.float32))
+    intr = torch.tensor([[[400., 400., 320., 240.]] * 2, [[517.97, 517.97, 320., 240.]] * 2])
+    _, _, _, Rg, tg = synth.two_view_geometry(B, 16, seed=78)
+    loftr_preds = torch.cat([Rg, tg[:, :, None]], dim=2).double()
+    num_corr = torch.tensor([350, 12])
+    with torch.no_grad():
+        feats, intr_s = ref.extract_features(images.clone(), intr.clone())
+        t, rot, Rm, r6 = ref(images.clone(), intr.clone(), loftr_num_corr=num_corr, loftr_preds=loftr_preds)
+        pos = O.emm_positional_encodings_vit(intr_s)
+        to, Ro, r6o, wto = O.vit_fusion_head(sd, feats, pos, loftr_preds, num_corr, mean, std)
+    close(to, t, 1e-4, "ViTEss t")
+    close(Ro, Rm, 1e-4, "ViTEss R")
+    close(r6o, r6, 1e-4, "ViTEss r6d")
+    npz("vit8pt.npz", t=t, R=Rm, r6d=r6, rot=rot, feats_s=feats[:, ::17, ::5], intr_scaled=intr_s, mean=mean, std=std,
+        loftr_preds=loftr_preds, num_corr=num_corr, intr=intr, seed=np.array([SEED, 20240003, 78]))
+
+
+def gen_mapfree_mlp():
+    """RegressionModel.regression_mlp (mapfree_6dreg/lib/models/regression/model.py:198-233): the method's own source
+    lines are executed on a stand-in `self` (building the whole model needs datasets/checkpoints that are not here)."""
+    print("[mapfree] reference RegressionModel.regression_mlp source, B=3")
+    import re
+    import types
+    src = open(os.path.join(R.REF_ROOT, "mapfree_6dreg/lib/models/regression/model.py")).read()
+    m = re.search(r"    def regression_mlp\(self.*?\n(?=    def )", src, flags=re.S)
+    body = "\n".join(line[4:] for line in m.group(0).splitlines())
+    loss_src = open(os.path.join(R.REF_ROOT, "mapfree_6dreg/lib/utils/loss.py")).read()
+    c6 = re.search(r"def compute_6d\(r\):.*?\n(?=\n)", loss_src, flags=re.S).group(0)
+    R.install_shims()
+    nsd = {"torch": torch}
+    exec(c6, nsd)
+    exec(body, nsd)
+    import torch.nn as nn
+    H, H2 = 256 * 12 * 9, 512
+    fake = types.SimpleNamespace(
+        use_prior=True, use_vanilla_transformer=True, num_corr_size=3,
+        pose_regressor=nn.Sequential(nn.Linear(H, H2), nn.ReLU(), nn.Linear(H2, H2), nn.ReLU(), nn.Linear(H2, 9)),
+        moe_predictor=nn.Sequential(nn.Linear(H + 18 + 3, H2), nn.ReLU(), nn.Linear(H2, H2), nn.ReLU(),
+                                    nn.Linear(H2, 2), nn.Sigmoid()))
+    sd = {}
+    for name in ("pose_regressor", "moe_predictor"):
+        mod = getattr(fake, name)
+        part = synth.synth_state_dict({f"{name}.{k}": v for k, v in mod.state_dict().items()}, SEED)
+        mod.load_state_dict({k[len(name) + 1:]: v for k, v in part.items()})
+        sd.update(part)
+    g = O.rng(31)
+    B = 3
+    feats = O.randn(g, B, 256, 12, 9)
+    _, _, _, Rg, tg = synth.two_view_geometry(B, 16, seed=79)
+    loftr_rt = torch.cat([Rg, 3.0 * tg[:, :, None]], dim=2)
+    inl = torch.tensor([[400., 120., 9.], [30., 2., 0.], [0., 0., 0.]])
+    with torch.no_grad():
+        Rr, tr = nsd["regression_mlp"](fake, feats, loftr_rt, inl)
+        Ro, to, wo = O.mapfree_regression_mlp(sd, feats.reshape(B, -1), loftr_rt, inl)
+    close(Ro, Rr, 1e-5, "mapfree R6d")
+    close(to, tr, 1e-5, "mapfree t")
+    npz("mapfree_mlp.npz", R=Rr, t=tr, loftr_rt=loftr_rt, inliers=inl, seed=np.array([SEED, 31, 79]))
+
+
 if __name__ == "__main__":
     assert R.have_reference(), "needs /root/reference (build container only)"
     torch.set_num_threads(os.cpu_count() or 1)
-    only = sys.argv[1:] or ["solver", "stages", "loftr_full"]
+    only = sys.argv[1:] or ["solver", "stages", "loftr_full", "vit8pt", "mapfree"]
     if "solver" in only:
         gen_solver()
     if "stages" in only:
         gen_stages()
     if "loftr_full" in only:
         gen_loftr_full()
+    if "vit8pt" in only:
+        gen_vit8pt()
+    if "mapfree" in only:
+        gen_mapfree_mlp()
     print("done")

@@ -360,3 +360,55 @@ def test_loftr_forward_full_vs_reference_golden(golden_dir):
     assert_close(data["regressed_rt"], torch.from_numpy(gold["regressed_rt"]), 1e-4, 1e-4, "regressed_rt")
     assert_close(data["gating_reg_weights"], torch.from_numpy(gold["gating"]), 1e-4, 0, "gating")
     assert_close(torch.from_numpy(data["priorRT"]), torch.from_numpy(gold["priorRT"]), 1e-4, 0, "priorRT")
+
+
+# ------------------------------------------------------------------------------------------- 8pt-ViT / map-free heads
+def _vit_args():
+    import types
+    return types.SimpleNamespace(pool_size=60, fc_hidden_size=512, use_loftr_gating=True, use_normalized_6d=True,
+                                 fusion_transformer=True, transformer_depth=6, T_pose=torch.tensor([[0., 0., 1.]]))
+
+
+def test_vitess_forward_vs_reference_golden(golden_dir):
+    """ViTEss.forward (B=2, 640x480) against the fixture from the unmodified reference; the transformer/EMM/MLP part
+    additionally against the oracle on the CUDA-extracted features (isolates cuDNN-vs-CPU conv differences)."""
+    from far_b200.vit8pt import ViTEss
+    gold = np.load(os.path.join(golden_dir, "vit8pt.npz"))
+    mean, std = torch.from_numpy(gold["mean"]), torch.from_numpy(gold["std"])
+    model = ViTEss(_vit_args(), mean, std)
+    sd = synth.synth_state_dict(model.state_dict(), int(gold["seed"][0]))
+    _load(model, sd)
+    g = np.random.default_rng(int(gold["seed"][1]))
+    images = torch.from_numpy(g.integers(0, 256, size=(2, 2, 3, 480, 640)).astype(np.float32))
+    intr = torch.from_numpy(gold["intr"])
+    lp, nc = torch.from_numpy(gold["loftr_preds"]), torch.from_numpy(gold["num_corr"])
+    with torch.no_grad():
+        feats, intr_s = model.extract_features(cu(images).clone(), intr.clone())
+        t, rot, R, r6 = model(cu(images), intr.clone(), loftr_num_corr=nc, loftr_preds=lp)
+        to, Ro, r6o, wto = O.vit_fusion_head(sd, feats.cpu(), O.emm_positional_encodings_vit(intr_s), lp, nc, mean, std)
+    assert_close(intr_s, torch.from_numpy(gold["intr_scaled"]), 1e-5, 0, "scaled intrinsics")
+    assert_close(feats[:, ::17, ::5], torch.from_numpy(gold["feats_s"]), 2e-4, 1e-4, "extracted features (cuDNN fp32)")
+    assert_close(t, to, 1e-4, 1e-4, "t vs oracle on same features")
+    assert_close(R, Ro, 1e-4, 0, "R vs oracle on same features")
+    assert_close(r6, r6o, 1e-4, 1e-4, "r6d vs oracle on same features")
+    assert_close(t, torch.from_numpy(gold["t"]), 1e-3, 1e-3, "t vs reference golden")
+    assert_close(R, torch.from_numpy(gold["R"]), 1e-3, 0, "R vs reference golden")
+    assert rot.shape == (2, 1, 3)
+
+
+def test_mapfree_regression_mlp_vs_reference_golden(golden_dir):
+    from far_b200.mapfree import RegressionHead
+    gold = np.load(os.path.join(golden_dir, "mapfree_mlp.npz"))
+    head = RegressionHead(use_prior=True)
+    sd = synth.synth_state_dict(head.state_dict(), int(gold["seed"][0]))
+    _load(head, sd)
+    g = O.rng(int(gold["seed"][1]))
+    feats = O.randn(g, 3, 256, 12, 9)
+    with torch.no_grad():
+        R, t = head.regression_mlp(cu(feats), torch.from_numpy(gold["loftr_rt"]), torch.from_numpy(gold["inliers"]))
+        Ro, to, _ = O.mapfree_regression_mlp(sd, feats.reshape(3, -1), torch.from_numpy(gold["loftr_rt"]),
+                                             torch.from_numpy(gold["inliers"]))
+    assert_close(R, Ro, 2e-5, 1e-4, "R6d vs oracle")
+    assert_close(t, to, 2e-5, 1e-4, "t vs oracle")
+    assert_close(R, torch.from_numpy(gold["R"]), 2e-5, 1e-4, "R6d vs reference golden")
+    assert_close(t, torch.from_numpy(gold["t"]), 2e-5, 1e-4, "t vs reference golden")

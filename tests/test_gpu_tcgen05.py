@@ -1,0 +1,50 @@
+"""The tcgen05 3xTF32 engine (far_b200/csrc/tc_gemm.cu: TMA -> UMMA kind::tf32 -> TMEM) against fp64 and against the
+fp32 CUDA-core engine.  3xTF32 must be fp32-accurate: the bar here is the SAME tolerance the CUDA-core engine meets."""
+import pytest
+import torch
+
+from oracle import far_oracle as O
+from far_b200 import ops
+from far_b200._lib import ACT_NONE, ACT_RELU, ACT_ELU1, ENGINE_SIMT, ENGINE_TCGEN05
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("M,N,K", [(4800, 512, 512), (4800, 256, 256), (1000, 768, 256), (5000, 256, 280),
+                                   (9600, 256, 512), (130, 4100, 64)])
+@pytest.mark.parametrize("act", [ACT_NONE, ACT_ELU1])
+def test_tc_linear_matches_fp64(M, N, K, act):
+    g = O.rng(M + N + K)
+    x, w, b = O.randn(g, M, K), O.randn(g, N, K, scale=K ** -0.5), O.randn(g, N, scale=0.1)
+    y = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), act, engine=ENGINE_TCGEN05)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    if act == ACT_ELU1:
+        ref = torch.nn.functional.elu(ref) + 1
+    assert_close(y, ref, 2e-5, 1e-5, f"tcgen05 linear {M}x{N}x{K}")
+    y2 = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), act, engine=ENGINE_SIMT)
+    # the two engines agree to fp32 rounding noise
+    assert_close(y, y2, 1e-5, 1e-5, "tcgen05 vs CUDA-core engine")
+
+
+def test_tc_linear_two_segments():
+    g = O.rng(77)
+    x1, x2 = O.randn(g, 4800, 256), O.randn(g, 4800, 256)
+    w = O.randn(g, 512, 512, scale=0.05)
+    y = ops.linear(x1.to(DEV), w.to(DEV), None, ACT_RELU, x2=x2.to(DEV), engine=ENGINE_TCGEN05)
+    ref = torch.relu(torch.nn.functional.linear(torch.cat([x1, x2], -1).double(), w.double()))
+    assert_close(y, ref, 2e-5, 1e-5, "tcgen05 two-segment linear")
+
+
+def test_tc_linear_adversarial_magnitudes():
+    """Mixed magnitudes / exact cancellation: the hi/lo split must not lose the small terms."""
+    g = O.rng(78)
+    x = O.randn(g, 1024, 256)
+    x[:, ::2] *= 1e3
+    x[:, 1::2] *= 1e-3
+    w = O.randn(g, 256, 256)
+    y = ops.linear(x.to(DEV), w.to(DEV), None, ACT_NONE, engine=ENGINE_TCGEN05)
+    ref = torch.nn.functional.linear(x.double(), w.double())
+    scale = ref.abs().max().item()
+    assert (y.double().cpu() - ref).abs().max().item() < 3e-6 * scale
