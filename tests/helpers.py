@@ -36,3 +36,12 @@ def pose_set_distance(R1, R2, t, R1o, R2o, to):
     b = torch.maximum((R1 - R2o).flatten(1).norm(dim=1), (R2 - R1o).flatten(1).norm(dim=1))
     dt = torch.minimum((t - to).norm(dim=1), (t + to).norm(dim=1))
     return torch.minimum(a, b), dt
+
+
+def f_distance(A, B):
+    """Sign/scale-invariant Frobenius distance between batches of 3x3 matrices."""
+    A = A.detach().double().cpu().reshape(-1, 9)
+    B = B.detach().double().cpu().reshape(-1, 9)
+    A = A / A.norm(dim=1, keepdim=True)
+    B = B / B.norm(dim=1, keepdim=True)
+    return torch.minimum((A - B).norm(dim=1), (A + B).norm(dim=1))

@@ -15,7 +15,7 @@ from far_b200 import ops, synth, solver as fsolver
 from far_b200._lib import ACT_NONE, ACT_RELU, ACT_GELU, ACT_ELU1, ACT_SIGMOID, ENGINE_SIMT
 from far_b200.loftr import (LoFTR, far_eval_cfg, LocalFeatureTransformer, CoarseMatching, FinePreprocess,
                             FineMatching, PositionEncodingSine, LocalFeatureTransformerRegressor)
-from tests.helpers import assert_close, f_normalize, pose_set_distance, maxdiff
+from tests.helpers import assert_close, f_normalize, f_distance, pose_set_distance, maxdiff
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -207,9 +207,9 @@ def test_eight_point_vs_oracle_and_golden(golden_dir):
     for weights, key in ((w, "F_w"), (None, "F_u")):
         F = fsolver.run_8point(cu(p1), cu(p2), cu(weights) if weights is not None else None)
         Fo = O.run_8point(p1.double(), p2.double(), weights.double() if weights is not None else None)
-        d = (f_normalize(F) - f_normalize(Fo)).flatten(1).norm(dim=1)
+        d = f_distance(F, Fo)
         assert d.max() < 1e-4, f"{key}: Frobenius distance to fp64 oracle {d.max():.3e}"
-        dg = (f_normalize(F) - f_normalize(torch.from_numpy(gold[key]))).flatten(1).norm(dim=1)
+        dg = f_distance(F, torch.from_numpy(gold[key]))
         assert dg.max() < 1e-3, f"{key}: Frobenius distance to reference fp32 golden {dg.max():.3e}"
         # the reference's own scale convention: F22 == 1 wherever |F22| > 1e-8
         assert_close(F[:, 2, 2], torch.ones(16), 1e-5, 0, "F22 normalisation")
@@ -226,7 +226,7 @@ def test_eight_point_properties_large():
     t = tg.double()
     tx[:, 0, 1], tx[:, 0, 2], tx[:, 1, 0], tx[:, 1, 2], tx[:, 2, 0], tx[:, 2, 1] = -t[:, 2], t[:, 1], t[:, 2], -t[:, 0], -t[:, 1], t[:, 0]
     Et = tx @ Rg.double()
-    d = (f_normalize(F) - f_normalize(Et)).flatten(1).norm(dim=1)
+    d = f_distance(F, Et)
     assert d.median() < 5e-3 and d.max() < 0.1, (d.median(), d.max())
 
 
