@@ -28,7 +28,7 @@ constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;     // 16 KiB per operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES; // Ahi, Alo, Bhi, Blo
 constexpr int NUM_THREADS = 192;
-constexpr int TMEM_COLS = 2 * BN;           // two accumulators
+constexpr int TMEM_COLS = 4 * BN;           // two accumulator buffers x (main hi*hi | small cross terms) = 512 columns
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -174,7 +174,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        // Tensor-core accumulation into fp32 rounds toward zero at every MMA (measured: a systematic ~K/8 * 3 * 2^-24
+        // relative shrink when all three product groups share one accumulator).  The 2^-11-times-smaller cross terms
+        // therefore get their own accumulator: the main one sees K/8 accumulation steps instead of 3K/8.
+        const uint32_t tmem_main = tmem_base + (uint32_t)(acc * 2 * BN);
+        const uint32_t tmem_small = tmem_main + (uint32_t)BN;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -186,9 +190,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128-byte swizzle row
-            umma_tf32(tmem_d, dAlo + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);  // small terms first
-            umma_tf32(tmem_d, dAhi + koff, dBlo + koff, kIdescTf32, 1u);
-            umma_tf32(tmem_d, dAhi + koff, dBhi + koff, kIdescTf32, 1u);
+            umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+            umma_tf32(tmem_small, dAhi + koff, dBlo + koff, kIdescTf32, 1u);
+            umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -211,8 +215,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
       const int row = m0 + quarter * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        uint32_t v[32], vs[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + (uint32_t)BN, vs);
         const int col0 = n0 + c * 32;
         if (row < p.M && col0 < p.N) {
           float* dst = p.C + (size_t)row * p.ldc + col0;
@@ -222,7 +228,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int col = col0 + j + e;
-              float t = __uint_as_float(v[j + e]);
+              float t = __uint_as_float(v[j + e]) + __uint_as_float(vs[j + e]);
               if (col < p.N) {
                 if (p.bias) t += __ldg(p.bias + col);
                 if (col < actc) t = apply_act(t, p.act);
@@ -318,9 +324,14 @@ bool tc_linear_supported(const float* x1, int ldx1, int K1, const float* x2, int
                          int M, int N) {
   (void)x1; (void)ldx1; (void)x2; (void)ldx2; (void)W;
   const int K = K1 + K2;
+  (void)M; (void)N;
   if (K % 4 != 0 || K < 32 || ldw != K) return false;         // TMA: 16-byte row pitch; weights contiguous
-  if ((long long)M * N < 128LL * 128 * 32) return false;      // small problems: CUDA-core engine (split-K, HBM-bound)
   return tc::get_encode() != nullptr;
+}
+
+bool tc_linear_preferred(int M, int N, int K) {
+  // small / skinny problems stay on the CUDA-core engine (split-K, HBM-bound on the weights)
+  return (long long)M * N >= 128LL * 128 * 32 && K <= 4096;
 }
 
 size_t tc_linear_workspace_bytes(int M, int N, int K) {

@@ -6,6 +6,7 @@ namespace far {
 // true when the shapes/strides satisfy the TMA + UMMA constraints of the engine
 bool tc_linear_supported(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
                          int M, int N);
+bool tc_linear_preferred(int M, int N, int K);
 // whether engine=0 (auto) should pick the tensor-core engine (env FAR_TC=0 disables)
 bool tc_engine_default_on();
 size_t tc_linear_workspace_bytes(int M, int N, int K);
