@@ -13,17 +13,18 @@
 // column max.  These differ only if two entries of one row are bit-identical maxima and the lower one loses its
 // column test -- a measure-zero event for real-valued features (documented in DESIGN.md).
 #include "score.cuh"
+#include "tc_score.cuh"
 
 namespace far {
 
 struct MatchLayout {  // byte offsets inside the workspace; the "sel" block depends on N*L only
   size_t flag, jsel, csel, bcount, boff, nblocks;
-  size_t rowlse, collse, rowmax, colmax, scratch, total;
+  size_t rowlse, collse, rowmax, colmax, scratch, tcws, tcws_bytes, total;
 };
 constexpr int kDecideThreads = 256;
 static inline size_t al(size_t v) { return (v + 255) & ~size_t(255); }
 
-static MatchLayout match_layout(int N, int L, int S) {
+static MatchLayout match_layout(int N, int L, int S, int C = 256) {
   MatchLayout m;
   const size_t R = (size_t)N * L;
   size_t off = 0;
@@ -40,6 +41,8 @@ static MatchLayout match_layout(int N, int L, int S) {
     m.rowmax = off; off += al((size_t)N * JT * L * 8);
     m.colmax = off; off += al((size_t)N * IT * S * 4);
     m.scratch = off; off += al(score_lse_scratch_floats(N, L, S) * 4);
+    m.tcws_bytes = tc_score_workspace_bytes(N, L, S, C);
+    m.tcws = off; off += al(m.tcws_bytes);
   }
   m.total = off;
   return m;
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(kDecideThreads) match_gather_kernel(
 using namespace far;
 
 extern "C" size_t far_dual_softmax_match_workspace_bytes(int N, int L, int S) {
-  return match_layout(N, L, S).total + 256;
+  return match_layout(N, L, S, 256).total + 256;  // sized for C <= 256 (the path's coarse width)
 }
 
 extern "C" int far_dual_softmax_match_select(const float* feat0, const float* feat1, int N, int L, int S, int C,
@@ -260,8 +263,8 @@ extern "C" int far_dual_softmax_match_select(const float* feat0, const float* fe
     return FAR_OK;
   }
   FAR_REQUIRE(feat0 && feat1 && workspace && C > 0 && h0c * w0c == L && h1c * w1c == S && temperature > 0.f);
-  (void)engine;
-  const MatchLayout m = match_layout(N, L, S);
+  FAR_REQUIRE(C <= 256);
+  const MatchLayout m = match_layout(N, L, S, 256);
   if (workspace_bytes < m.total) return FAR_ERR_WORKSPACE;
   char* base = reinterpret_cast<char*>(workspace);
   float* rowlse = reinterpret_cast<float*>(base + m.rowlse);
@@ -273,7 +276,9 @@ extern "C" int far_dual_softmax_match_select(const float* feat0, const float* fe
   a.H = 1; a.G = N; a.L = L; a.S = S; a.K = C;
   // sim = (f0 / sqrt(C)) . (f1 / sqrt(C)) / T   (:108-113)
   a.scale = 1.0f / ((float)C * temperature);
-  int rc = score_lse(a, rowlse, collse, reinterpret_cast<float*>(base + m.scratch), st);
+  float* tcws = (engine == 1) ? nullptr : reinterpret_cast<float*>(base + m.tcws);
+  int used_tc = 0;
+  int rc = score_lse(a, rowlse, collse, reinterpret_cast<float*>(base + m.scratch), st, tcws, m.tcws_bytes, &used_tc);
   if (rc) return rc;
 
   ConfArgs p;
@@ -284,12 +289,17 @@ extern "C" int far_dual_softmax_match_select(const float* feat0, const float* fe
   p.colmax = reinterpret_cast<float*>(base + m.colmax);
   p.conf_out = conf_out;
   const int IT = score_tiles_i(L), JT = score_tiles_j(S);
-  dim3 grid(JT, IT, N);
-  if (score_vec_ok(a))
-    match_conf_kernel<true><<<grid, kTileThreads, 0, st>>>(p);
-  else
-    match_conf_kernel<false><<<grid, kTileThreads, 0, st>>>(p);
-  FAR_CHECK_LAUNCH();
+  if (used_tc) {  // operands are already split in tcws by the LSE pass
+    rc = tc_match_conf(a, rowlse, collse, p.rowmax, p.colmax, conf_out, tcws, m.tcws_bytes, 1, st);
+    if (rc) return rc;
+  } else {
+    dim3 grid(JT, IT, N);
+    if (score_vec_ok(a))
+      match_conf_kernel<true><<<grid, kTileThreads, 0, st>>>(p);
+    else
+      match_conf_kernel<false><<<grid, kTileThreads, 0, st>>>(p);
+    FAR_CHECK_LAUNCH();
+  }
 
   int* flag = reinterpret_cast<int*>(base + m.flag);
   int* jsel = reinterpret_cast<int*>(base + m.jsel);

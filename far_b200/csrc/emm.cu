@@ -12,6 +12,7 @@
 //                          partial  F_it = V'_i^T T  goes to the workspace
 //   reduce                 F = sum_it F_it (fixed order)
 #include "score.cuh"
+#include "tc_score.cuh"
 
 namespace far {
 
@@ -175,7 +176,7 @@ __global__ void emm_reduce_kernel(const float* __restrict__ Fpart, int IT, int d
 }
 
 static inline size_t al(size_t v) { return (v + 255) & ~size_t(255); }
-struct EmmPlan { size_t rowlse, collse, fpart, scratch, total; };
+struct EmmPlan { size_t rowlse, collse, fpart, scratch, tcws, tcws_bytes, total; };
 static EmmPlan emm_plan(int B, int N, int h, int d) {
   EmmPlan p; size_t off = 0;
   const int G = B * h, IT = score_tiles_i(N), dv = d + 6;
@@ -183,12 +184,14 @@ static EmmPlan emm_plan(int B, int N, int h, int d) {
   p.collse = off;  off += al((size_t)G * N * 4);
   p.fpart = off;   off += al((size_t)G * IT * dv * dv * 4);
   p.scratch = off; off += al(score_lse_scratch_floats(G, N, N) * 4);
+  p.tcws_bytes = tc_score_workspace_bytes(G, N, N, d);
+  p.tcws = off; off += al(p.tcws_bytes);
   p.total = off;
   return p;
 }
 
 static int emm_one_direction(const float* qkv_q, const float* qkv_kv, const float* pos, int Bpos, int B, int N, int h,
-                             int d, float scale, float* F, char* base, const EmmPlan& pl, cudaStream_t st) {
+                             int d, float scale, float* F, char* base, const EmmPlan& pl, int engine, cudaStream_t st) {
   const int C = h * d, G = B * h, IT = score_tiles_i(N), dv = d + 6;
   EmmArgs p;
   ScoreArgs& a = p.sc;
@@ -197,7 +200,8 @@ static int emm_one_direction(const float* qkv_q, const float* qkv_kv, const floa
   a.H = h; a.G = G; a.L = N; a.S = N; a.K = d; a.scale = scale;
   float* rowlse = reinterpret_cast<float*>(base + pl.rowlse);
   float* collse = reinterpret_cast<float*>(base + pl.collse);
-  int rc = score_lse(a, rowlse, collse, reinterpret_cast<float*>(base + pl.scratch), st);
+  int rc = score_lse(a, rowlse, collse, reinterpret_cast<float*>(base + pl.scratch), st,
+                     engine == 1 ? nullptr : reinterpret_cast<float*>(base + pl.tcws), pl.tcws_bytes);
   if (rc) return rc;
   p.v = qkv_kv + 2 * C;  // v = qkv[..., 2, :, :]
   p.pos = pos; p.Bpos = Bpos; p.d = d;
@@ -234,15 +238,14 @@ extern "C" int far_emm_bilinear_attn(const float* qkv1, const float* qkv2, const
   if (B <= 0) return FAR_OK;
   FAR_REQUIRE(qkv1 && qkv2 && pos && F1 && F2 && workspace && Ntok > 0 && h > 0 && d > 0 && d + 6 <= EDV &&
               (Bpos == 1 || Bpos == B));
-  (void)engine;
   const EmmPlan pl = emm_plan(B, Ntok, h, d);
   if (workspace_bytes < pl.total) return FAR_ERR_WORKSPACE;
   char* base = reinterpret_cast<char*>(workspace);
   cudaStream_t st = (cudaStream_t)stream;
   // attn_1 = q2 k1^T, values v1  -> fundamental_1 ; attn_2 = q1 k2^T, values v2 -> fundamental_2  (:275-292)
-  int rc = emm_one_direction(qkv2, qkv1, pos, Bpos, B, Ntok, h, d, scale, F1, base, pl, st);
+  int rc = emm_one_direction(qkv2, qkv1, pos, Bpos, B, Ntok, h, d, scale, F1, base, pl, engine, st);
   if (rc) return rc;
-  return emm_one_direction(qkv1, qkv2, pos, Bpos, B, Ntok, h, d, scale, F2, base, pl, st);
+  return emm_one_direction(qkv1, qkv2, pos, Bpos, B, Ntok, h, d, scale, F2, base, pl, engine, st);
 }
 
 // timm Attention core (interiornetStreetlearn_8ptVit/src/modules/vision_transformer.py:250-257)

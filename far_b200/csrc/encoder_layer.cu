@@ -1,6 +1,7 @@
 // LoFTREncoderLayer.forward (mp3d_loftr/src/loftr/loftr_module/transformer.py:44-67), masks None.
 // Host-side composition of the library's own kernels so the Python side makes one C-ABI call per layer.
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace far {
 int linear_dispatch(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
@@ -14,7 +15,7 @@ size_t linear_attention_ws_bytes(int N, int S, int H, int D);
 static inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct LayerPlan {
-  size_t q, k, v, attn, msg, hid, la, total;
+  size_t q, k, v, attn, msg, hid, la, lin, lin_bytes, total;
 };
 static LayerPlan plan_layer(long long N, int L, int S, int C, int nhead) {
   LayerPlan p;
@@ -27,6 +28,10 @@ static LayerPlan plan_layer(long long N, int L, int S, int C, int nhead) {
   p.msg = off; off += align_up(rowsL * C * 4);
   p.hid = off; off += align_up(rowsL * 2 * C * 4);
   p.la = off; off += align_up(linear_attention_ws_bytes((int)N, S, nhead, C / nhead));
+  // hi/lo operand split of the tcgen05 engine, sized for the layer's largest GEMM (mlp.0: [rows, 2C] x [2C, 2C])
+  const size_t rows = rowsL > rowsS ? rowsL : rowsS;
+  p.lin_bytes = tc_linear_workspace_bytes((int)rows, 2 * C, 2 * C);
+  p.lin = off; off += align_up(p.lin_bytes);
   p.total = off;
   return p;
 }
@@ -54,20 +59,22 @@ extern "C" int far_loftr_encoder_layer(const float* x, const float* source, floa
   float* msg = reinterpret_cast<float*>(base + p.msg);
   float* hid = reinterpret_cast<float*>(base + p.hid);
   float* la = reinterpret_cast<float*>(base + p.la);
+  float* lw = reinterpret_cast<float*>(base + p.lin);
+  const size_t lwb = p.lin_bytes;
   const int ML = N * L, MS = N * S, D = C / nhead;
   int rc;
   // q/k projections with the elu(x)+1 feature map fused into the epilogue; v plain (:55-57, linear_attention.py:33-34)
-  if ((rc = linear_dispatch(x, C, C, nullptr, 0, 0, w->wq, C, nullptr, q, C, ML, C, FAR_ACT_ELU1, -1, engine, nullptr, 0, st))) return rc;
-  if ((rc = linear_dispatch(source, C, C, nullptr, 0, 0, w->wk, C, nullptr, k, C, MS, C, FAR_ACT_ELU1, -1, engine, nullptr, 0, st))) return rc;
-  if ((rc = linear_dispatch(source, C, C, nullptr, 0, 0, w->wv, C, nullptr, v, C, MS, C, FAR_ACT_NONE, -1, engine, nullptr, 0, st))) return rc;
+  if ((rc = linear_dispatch(x, C, C, nullptr, 0, 0, w->wq, C, nullptr, q, C, ML, C, FAR_ACT_ELU1, -1, engine, lw, lwb, st))) return rc;
+  if ((rc = linear_dispatch(source, C, C, nullptr, 0, 0, w->wk, C, nullptr, k, C, MS, C, FAR_ACT_ELU1, -1, engine, lw, lwb, st))) return rc;
+  if ((rc = linear_dispatch(source, C, C, nullptr, 0, 0, w->wv, C, nullptr, v, C, MS, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
   if ((rc = linear_attention_dispatch(q, C, k, C, v, C, attn, C, N, L, S, nhead, D, 1e-6f, 1, la,
                                       workspace_bytes - p.la, st))) return rc;
   // merge + norm1 (:58-59)
-  if ((rc = linear_dispatch(attn, C, C, nullptr, 0, 0, w->wmerge, C, nullptr, msg, C, ML, C, FAR_ACT_NONE, -1, engine, nullptr, 0, st))) return rc;
+  if ((rc = linear_dispatch(attn, C, C, nullptr, 0, 0, w->wmerge, C, nullptr, msg, C, ML, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
   if ((rc = far_layernorm(msg, w->g1, w->b1, nullptr, attn, ML, C, 1e-5f, stream))) return rc;  // attn := LN(msg)
   // mlp([x | message]) (:62-63): two K-segments instead of a materialised concat
-  if ((rc = linear_dispatch(x, C, C, attn, C, C, w->wmlp0, 2 * C, nullptr, hid, 2 * C, ML, 2 * C, FAR_ACT_RELU, -1, engine, nullptr, 0, st))) return rc;
-  if ((rc = linear_dispatch(hid, 2 * C, 2 * C, nullptr, 0, 0, w->wmlp2, 2 * C, nullptr, msg, C, ML, C, FAR_ACT_NONE, -1, engine, nullptr, 0, st))) return rc;
+  if ((rc = linear_dispatch(x, C, C, attn, C, C, w->wmlp0, 2 * C, nullptr, hid, 2 * C, ML, 2 * C, FAR_ACT_RELU, -1, engine, lw, lwb, st))) return rc;
+  if ((rc = linear_dispatch(hid, 2 * C, 2 * C, nullptr, 0, 0, w->wmlp2, 2 * C, nullptr, msg, C, ML, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
   // norm2 + residual (:64-66)
   return far_layernorm(msg, w->g2, w->b2, x, out, ML, C, 1e-5f, stream);
 }

@@ -1,4 +1,5 @@
 #include "score.cuh"
+#include "tc_score.cuh"
 
 namespace far {
 
@@ -76,16 +77,24 @@ __global__ void lse_finalize_kernel(const float2* __restrict__ part, int tiles, 
   lse[idx] = v.m + logf(v.s);
 }
 
-int score_lse(const ScoreArgs& a, float* row_lse, float* col_lse, float* scratch, cudaStream_t st) {
+int score_lse(const ScoreArgs& a, float* row_lse, float* col_lse, float* scratch, cudaStream_t st, float* tcws,
+              size_t tcws_bytes, int* used_tc) {
   const int IT = score_tiles_i(a.L), JT = score_tiles_j(a.S);
   float2* rowpart = reinterpret_cast<float2*>(scratch);
   float2* colpart = rowpart + (size_t)a.G * JT * a.L;
-  dim3 grid(JT, IT, a.G);
-  if (score_vec_ok(a))
-    score_lse_kernel<true><<<grid, kTileThreads, 0, st>>>(a, rowpart, colpart);
-  else
-    score_lse_kernel<false><<<grid, kTileThreads, 0, st>>>(a, rowpart, colpart);
-  FAR_CHECK_LAUNCH();
+  const bool use_tc = tcws != nullptr && tcws_bytes >= tc_score_workspace_bytes(a.G, a.L, a.S, a.K) && tc_score_supported(a);
+  if (used_tc) *used_tc = use_tc ? 1 : 0;
+  if (use_tc) {
+    int rc = tc_score_lse_partials(a, rowpart, colpart, tcws, tcws_bytes, 0, st);
+    if (rc) return rc;
+  } else {
+    dim3 grid(JT, IT, a.G);
+    if (score_vec_ok(a))
+      score_lse_kernel<true><<<grid, kTileThreads, 0, st>>>(a, rowpart, colpart);
+    else
+      score_lse_kernel<false><<<grid, kTileThreads, 0, st>>>(a, rowpart, colpart);
+    FAR_CHECK_LAUNCH();
+  }
   const long long tr = (long long)a.G * a.L, tc = (long long)a.G * a.S;
   lse_finalize_kernel<<<(unsigned)ceil_div_ll(tr, 256), 256, 0, st>>>(rowpart, JT, a.L, tr, row_lse);
   FAR_CHECK_LAUNCH();

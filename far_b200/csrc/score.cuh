@@ -27,7 +27,11 @@ inline size_t score_lse_scratch_floats(int G, int L, int S) {
 }
 
 // Computes row_lse [G][L] and col_lse [G][S].  `scratch` >= score_lse_scratch_floats().
-int score_lse(const ScoreArgs& a, float* row_lse, float* col_lse, float* scratch, cudaStream_t st);
+// When `tcws` (>= tc_score_workspace_bytes) is given and the shape qualifies, the tile pass runs on the tcgen05
+// 3xTF32 pipeline (tc_score.cu) and leaves the hi/lo-split operands in `tcws` for a following recompute pass.
+// *used_tc (optional) reports which engine ran.
+int score_lse(const ScoreArgs& a, float* row_lse, float* col_lse, float* scratch, cudaStream_t st,
+              float* tcws = nullptr, size_t tcws_bytes = 0, int* used_tc = nullptr);
 
 // Device helper: this thread's 8x8 scaled scores of the tile at (i0, j0) of group g.
 template <bool kVec4>

@@ -1,0 +1,351 @@
+// Dual-softmax score passes on the tcgen05 3xTF32 pipeline (same TMA -> UMMA -> TMEM structure as tc_gemm.cu):
+//   MODE_LSE  : S tile -> per-row / per-column (max, sumexp) partials           (pass A of score.cu)
+//   MODE_CONF : S tile -> conf = exp(s-rowlse) exp(s-collse), per-row (max, argmax) and per-column max partials,
+//               optional dense conf output                                       (pass B of coarse_match.cu)
+// Outputs have exactly the layout of the CUDA-core kernels (score_lse_kernel / match_conf_kernel), so the merge /
+// decide / gather kernels downstream are shared.  In the TMEM accumulator a thread owns one ROW of the tile
+// (tcgen05.ld 32x32b), so row reductions are thread-local; column reductions go through a 128 x 33 shared-memory
+// transpose (bank-conflict free) synchronised with a named barrier among the 128 epilogue threads.
+#include "score.cuh"
+#include "tc_common.cuh"
+#include "tc_score.cuh"
+#include "tc_gemm.cuh"
+
+namespace far {
+namespace tc {
+
+constexpr int MODE_LSE = 0, MODE_CONF = 1;
+constexpr int SPITCH = 33;
+constexpr size_t SCORE_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + 256 + (size_t)BM * SPITCH * 4 + 4 * 32 * 8 + BN * 4;
+
+struct ScoreTcArgs {
+  int G, H, L, S, K;       // groups (= nb * H), heads per batch, rows of A, rows of B, contraction
+  float scale;
+  // MODE_LSE outputs
+  float2* rowpart;         // [(g*JT + jt)*L + i] (m, s)
+  float2* colpart;         // [(g*IT + it)*S + j]
+  // MODE_CONF inputs / outputs
+  const float* rowlse;     // [G][L]
+  const float* collse;     // [G][S]
+  float2* rowmax;          // [(g*JT + jt)*L + i] (conf, bits(j))
+  float* colmax;           // [(g*IT + it)*S + j]
+  float* conf_out;         // optional [G][L][S]
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, ScoreTcArgs p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  unsigned char* gen = smem_dyn + (bar_base + 256 - raw);  // generic pointer to the epilogue scratch
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - raw));
+  float(*scr)[SPITCH] = reinterpret_cast<float(*)[SPITCH]>(gen);
+  float2(*part)[32] = reinterpret_cast<float2(*)[32]>(gen + (size_t)BM * SPITCH * 4);
+  float* cls = reinterpret_cast<float*>(gen + (size_t)BM * SPITCH * 4 + 4 * 32 * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int IT = (p.L + BM - 1) / BM, JT = (p.S + BN - 1) / BN;
+  const int num_tiles = p.G * IT * JT;
+  const int kblocks = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int jt = tile % JT, it = (tile / JT) % IT, g = tile / (JT * IT);
+        const int g0 = g % p.H, g1 = g / p.H;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sbase = base + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_4d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, it * BM, g0, g1);
+          tma_load_4d(sbase + 1 * TILE_BYTES, &mapAlo, full_bar(stage), kb * BK, it * BM, g0, g1);
+          tma_load_4d(sbase + 2 * TILE_BYTES, &mapBhi, full_bar(stage), kb * BK, jt * BN, g0, g1);
+          tma_load_4d(sbase + 3 * TILE_BYTES, &mapBlo, full_bar(stage), kb * BK, jt * BN, g0, g1);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_main = tmem_base + (uint32_t)(acc * 2 * BN);
+        const uint32_t tmem_small = tmem_main + (uint32_t)BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sbase = base + stage * STAGE_BYTES;
+          const uint64_t dAhi = make_kmajor_sw128_desc(sbase + 0 * TILE_BYTES);
+          const uint64_t dAlo = make_kmajor_sw128_desc(sbase + 1 * TILE_BYTES);
+          const uint64_t dBhi = make_kmajor_sw128_desc(sbase + 2 * TILE_BYTES);
+          const uint64_t dBlo = make_kmajor_sw128_desc(sbase + 3 * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+            umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+            umma_tf32(tmem_small, dAhi + koff, dBlo + koff, kIdescTf32, 1u);
+            umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue: 128 threads, thread = tile row =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;       // row inside the tile
+    const int et = (warp - 2) * 32 + lane;     // 0..127 dense epilogue thread id (column-phase mapping)
+    const int ce = et & 31, cq = et >> 5;      // column-phase: column ce of the chunk, rows [32*cq, 32*cq + 32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int jt = tile % JT, it = (tile / JT) % IT, g = tile / (JT * IT);
+      const int i0 = it * BM, j0 = jt * BN;
+      const int grow = i0 + row;
+      const bool rvalid = grow < p.L;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      float rl = 0.f;
+      if (MODE == MODE_CONF) {
+        rl = rvalid ? p.rowlse[(size_t)g * p.L + grow] : 0.f;
+        const int c = j0 + et;
+        cls[et] = (c < p.S) ? p.collse[(size_t)g * p.S + c] : 0.f;
+        epi_bar();
+      }
+      float m_r = -INFINITY, s_r = 0.f;   // MODE_LSE row accumulators
+      float bv = -1.f;                     // MODE_CONF row (max, argmax)
+      int bj = 0x7fffffff;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32], vs[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + (uint32_t)BN, vs);
+        const int col0 = j0 + c * 32;
+        float x[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) x[e] = (__uint_as_float(v[e]) + __uint_as_float(vs[e])) * p.scale;
+        if (MODE == MODE_LSE) {
+          float cm = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (col0 + e < p.S) cm = fmaxf(cm, x[e]);
+          if (rvalid && cm > -INFINITY) {
+            const float nm = fmaxf(m_r, cm);
+            float acc_s = (m_r == -INFINITY) ? 0.f : s_r * expf(m_r - nm);
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (col0 + e < p.S) acc_s += expf(x[e] - nm);
+            m_r = nm;
+            s_r = acc_s;
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) scr[row][e] = rvalid ? x[e] : -INFINITY;
+          epi_bar();
+          {  // column phase: (max, sumexp) over 32 rows of one column
+            float pm = -INFINITY;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) pm = fmaxf(pm, scr[cq * 32 + r][ce]);
+            float ps = 0.f;
+            if (pm > -INFINITY) {
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) ps += expf(scr[cq * 32 + r][ce] - pm);  // exp(-inf) = 0 for masked rows
+            }
+            part[cq][ce] = make_float2(pm, ps);
+          }
+          epi_bar();
+          if (et < 32) {
+            MS a = ms_init();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a = ms_merge(a, MS{part[q][et].x, part[q][et].y});
+            const int col = col0 + et;
+            if (col < p.S) p.colpart[((size_t)g * IT + it) * p.S + col] = make_float2(a.m, a.s);
+          }
+          epi_bar();
+        } else {
+          // conf = softmax(sim, 1) * softmax(sim, 2)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int col = col0 + e;
+            const bool ok = rvalid && col < p.S;
+            x[e] = ok ? expf(x[e] - rl) * expf(x[e] - cls[c * 32 + e]) : -1.f;
+            if (x[e] > bv) { bv = x[e]; bj = col; }   // ascending columns, strict > keeps the lowest j on ties
+          }
+          if (p.conf_out != nullptr && rvalid) {
+            float* dst = p.conf_out + ((size_t)g * p.L + grow) * p.S + col0;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (col0 + e < p.S) dst[e] = x[e];
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) scr[row][e] = x[e];
+          epi_bar();
+          {
+            float pm = -1.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) pm = fmaxf(pm, scr[cq * 32 + r][ce]);
+            part[cq][ce] = make_float2(pm, 0.f);
+          }
+          epi_bar();
+          if (et < 32) {
+            float a = fmaxf(fmaxf(part[0][et].x, part[1][et].x), fmaxf(part[2][et].x, part[3][et].x));
+            const int col = col0 + et;
+            if (col < p.S) p.colmax[((size_t)g * IT + it) * p.S + col] = a;
+          }
+          epi_bar();
+        }
+      }
+      if (rvalid) {
+        if (MODE == MODE_LSE) p.rowpart[((size_t)g * JT + jt) * p.L + grow] = make_float2(m_r, s_r);
+        else p.rowmax[((size_t)g * JT + jt) * p.L + grow] = make_float2(bv, __int_as_float(bj));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// hi/lo split of a strided operand set: copies group (b,h) rows [rows x K] into dense [G][rows][K] arrays
+__global__ void split_groups_kernel(const float* __restrict__ x, long long sb, long long sh, int ld, int H, int G,
+                                    int rows, int K, float* __restrict__ hi, float* __restrict__ lo) {
+  const long long total = (long long)G * rows * K;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % K);
+    const long long t = idx / K;
+    const int r = (int)(t % rows);
+    const int g = (int)(t / rows);
+    const float v = x[(size_t)(g / H) * sb + (size_t)(g % H) * sh + (size_t)r * ld + k];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[idx] = h;
+    lo[idx] = v - h;
+  }
+}
+
+struct SplitOps { float *ahi, *alo, *bhi, *blo; };
+
+static int prepare_operands(const ScoreArgs& a, float* ws, size_t ws_bytes, SplitOps* o, CUtensorMap maps[4],
+                            int split_done, cudaStream_t st) {
+  const size_t na = al((size_t)a.G * a.L * a.K * 4), nb = al((size_t)a.G * a.S * a.K * 4);
+  if (ws == nullptr || ws_bytes < 2 * na + 2 * nb + 1024) return FAR_ERR_WORKSPACE;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+  o->ahi = reinterpret_cast<float*>(base);
+  o->alo = reinterpret_cast<float*>(base + na);
+  o->bhi = reinterpret_cast<float*>(base + 2 * na);
+  o->blo = reinterpret_cast<float*>(base + 2 * na + nb);
+  if (!split_done) {
+    const int blocks = kNumSMs * 8;
+    split_groups_kernel<<<blocks, 256, 0, st>>>(a.A, a.sAb, a.sAh, a.lda, a.H, a.G, a.L, a.K, o->ahi, o->alo);
+    FAR_CHECK_LAUNCH();
+    split_groups_kernel<<<blocks, 256, 0, st>>>(a.B, a.sBb, a.sBh, a.ldb, a.H, a.G, a.S, a.K, o->bhi, o->blo);
+    FAR_CHECK_LAUNCH();
+  }
+  // dense [G][rows][K]: 4-D map dims (K, rows, H, G/H)
+  const int nbat = a.G / a.H;
+  const bool ok = make_map4(&maps[0], o->ahi, a.K, a.L, a.K, a.H, (long long)a.L * a.K, nbat, (long long)a.H * a.L * a.K) &&
+                  make_map4(&maps[1], o->alo, a.K, a.L, a.K, a.H, (long long)a.L * a.K, nbat, (long long)a.H * a.L * a.K) &&
+                  make_map4(&maps[2], o->bhi, a.K, a.S, a.K, a.H, (long long)a.S * a.K, nbat, (long long)a.H * a.S * a.K) &&
+                  make_map4(&maps[3], o->blo, a.K, a.S, a.K, a.H, (long long)a.S * a.K, nbat, (long long)a.H * a.S * a.K);
+  return ok ? FAR_OK : FAR_ERR_CUDA;
+}
+
+static void set_attr_once() {
+  static bool done = false;
+  if (!done) {
+    cudaFuncSetAttribute(tc_score_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM);
+    cudaFuncSetAttribute(tc_score_kernel<MODE_CONF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM);
+    done = true;
+  }
+}
+
+}  // namespace tc
+
+bool tc_score_supported(const ScoreArgs& a) {
+  return a.K % 4 == 0 && a.K >= 32 && a.G % a.H == 0 && tc::get_encode() != nullptr && tc_engine_default_on();
+}
+
+size_t tc_score_workspace_bytes(int G, int L, int S, int K) {
+  return 2 * tc::al((size_t)G * L * K * 4) + 2 * tc::al((size_t)G * S * K * 4) + 4096;
+}
+
+int tc_score_lse_partials(const ScoreArgs& a, float2* rowpart, float2* colpart, float* ws, size_t ws_bytes,
+                          int split_done, cudaStream_t st) {
+  using namespace tc;
+  SplitOps o;
+  CUtensorMap maps[4];
+  int rc = prepare_operands(a, ws, ws_bytes, &o, maps, split_done, st);
+  if (rc) return rc;
+  set_attr_once();
+  ScoreTcArgs p{};
+  p.G = a.G; p.H = a.H; p.L = a.L; p.S = a.S; p.K = a.K; p.scale = a.scale;
+  p.rowpart = rowpart; p.colpart = colpart;
+  const int tiles = a.G * ceil_div(a.L, BM) * ceil_div(a.S, BN);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  tc_score_kernel<MODE_LSE><<<grid, NUM_THREADS, SCORE_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+int tc_match_conf(const ScoreArgs& a, const float* rowlse, const float* collse, float2* rowmax, float* colmax,
+                  float* conf_out, float* ws, size_t ws_bytes, int split_done, cudaStream_t st) {
+  using namespace tc;
+  SplitOps o;
+  CUtensorMap maps[4];
+  int rc = prepare_operands(a, ws, ws_bytes, &o, maps, split_done, st);
+  if (rc) return rc;
+  set_attr_once();
+  ScoreTcArgs p{};
+  p.G = a.G; p.H = a.H; p.L = a.L; p.S = a.S; p.K = a.K; p.scale = a.scale;
+  p.rowlse = rowlse; p.collse = collse; p.rowmax = rowmax; p.colmax = colmax; p.conf_out = conf_out;
+  const int tiles = a.G * ceil_div(a.L, BM) * ceil_div(a.S, BN);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  tc_score_kernel<MODE_CONF><<<grid, NUM_THREADS, SCORE_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+}  // namespace far

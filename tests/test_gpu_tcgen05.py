@@ -52,3 +52,17 @@ def test_tc_linear_adversarial_magnitudes():
     ref = torch.nn.functional.linear(x.double(), w.double())
     scale = ref.abs().max().item()
     assert (y.double().cpu() - ref).abs().max().item() < 3e-6 * scale
+
+
+@pytest.mark.parametrize("engine", [ENGINE_SIMT, 0])
+def test_dual_softmax_match_both_engines(engine):
+    """CoarseMatching on the CUDA-core engine and on the tcgen05 score passes: identical ordered indices vs the oracle."""
+    g = O.rng(61)
+    c0, c1 = O.randn(g, 2, 40 * 50, 256, scale=3.0), O.randn(g, 2, 36 * 44, 256, scale=3.0)
+    m = ops.dual_softmax_match(c0.to(DEV), c1.to(DEV), (40, 50), (36, 44), 0.0, 2, 0.1, 8.0, 8.0,
+                               return_conf_matrix=True, engine=engine)
+    o = O.coarse_matching(c0, c1, (40, 50), (36, 44), 0.0, 2, 0.1, 8.0)
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(m[k].cpu(), o[k]), (k, m[k].numel(), o[k].numel())
+    assert_close(m["mconf"], o["mconf"], 1e-6, 1e-4, "mconf")
+    assert_close(m["conf_matrix"], o["conf_matrix"], 1e-7, 1e-4, "conf_matrix")
