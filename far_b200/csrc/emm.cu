@@ -13,6 +13,7 @@
 //   reduce                 F = sum_it F_it (fixed order)
 #include "score.cuh"
 #include "tc_score.cuh"
+#include "tc_emm.cuh"
 
 namespace far {
 
@@ -176,7 +177,7 @@ __global__ void emm_reduce_kernel(const float* __restrict__ Fpart, int IT, int d
 }
 
 static inline size_t al(size_t v) { return (v + 255) & ~size_t(255); }
-struct EmmPlan { size_t rowlse, collse, fpart, scratch, tcws, tcws_bytes, total; };
+struct EmmPlan { size_t rowlse, collse, fpart, scratch, tcws, tcws_bytes, vtws, vtws_bytes, total; };
 static EmmPlan emm_plan(int B, int N, int h, int d) {
   EmmPlan p; size_t off = 0;
   const int G = B * h, IT = score_tiles_i(N), dv = d + 6;
@@ -186,6 +187,8 @@ static EmmPlan emm_plan(int B, int N, int h, int d) {
   p.scratch = off; off += al(score_lse_scratch_floats(G, N, N) * 4);
   p.tcws_bytes = tc_score_workspace_bytes(G, N, N, d);
   p.tcws = off; off += al(p.tcws_bytes);
+  p.vtws_bytes = tc_emm_vt_bytes(G, N);
+  p.vtws = off; off += al(p.vtws_bytes);
   p.total = off;
   return p;
 }
@@ -200,10 +203,24 @@ static int emm_one_direction(const float* qkv_q, const float* qkv_kv, const floa
   a.H = h; a.G = G; a.L = N; a.S = N; a.K = d; a.scale = scale;
   float* rowlse = reinterpret_cast<float*>(base + pl.rowlse);
   float* collse = reinterpret_cast<float*>(base + pl.collse);
-  int rc = score_lse(a, rowlse, collse, reinterpret_cast<float*>(base + pl.scratch), st,
-                     engine == 1 ? nullptr : reinterpret_cast<float*>(base + pl.tcws), pl.tcws_bytes);
+  int used_tc = 0;
+  float* tcws = engine == 1 ? nullptr : reinterpret_cast<float*>(base + pl.tcws);
+  int rc = score_lse(a, rowlse, collse, reinterpret_cast<float*>(base + pl.scratch), st, tcws, pl.tcws_bytes, &used_tc);
   if (rc) return rc;
   p.v = qkv_kv + 2 * C;  // v = qkv[..., 2, :, :]
+  if (used_tc && tc_emm_supported(N, d) && !getenv("FAR_EMM_SIMT")) {
+    // fused tcgen05 recompute pass: S, P (in TMEM) and T = P V' all on the tensor pipe
+    float *qhi, *qlo, *khi, *klo;
+    tc_score_operand_ptrs(a, tcws, &qhi, &qlo, &khi, &klo);
+    float* Fpart = reinterpret_cast<float*>(base + pl.fpart);
+    rc = tc_emm_pv(qhi, qlo, khi, klo, p.v, a.sBb, a.sBh, a.ldb, pos, Bpos, G, h, N, d, scale, rowlse, collse, Fpart,
+                   reinterpret_cast<float*>(base + pl.vtws), pl.vtws_bytes, st);
+    if (rc) return rc;
+    const long long total = (long long)G * dv * dv;
+    emm_reduce_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(Fpart, IT, dv * dv, total, F);
+    FAR_CHECK_LAUNCH();
+    return FAR_OK;
+  }
   p.pos = pos; p.Bpos = Bpos; p.d = d;
   p.rowlse = rowlse; p.collse = collse;
   p.Fpart = reinterpret_cast<float*>(base + pl.fpart);

@@ -308,6 +308,15 @@ bool tc_score_supported(const ScoreArgs& a) {
   return a.K % 4 == 0 && a.K >= 32 && a.G % a.H == 0 && tc::get_encode() != nullptr && tc_engine_default_on();
 }
 
+void tc_score_operand_ptrs(const ScoreArgs& a, float* ws, float** ahi, float** alo, float** bhi, float** blo) {
+  const size_t na = tc::al((size_t)a.G * a.L * a.K * 4), nb = tc::al((size_t)a.G * a.S * a.K * 4);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+  *ahi = reinterpret_cast<float*>(base);
+  *alo = reinterpret_cast<float*>(base + na);
+  *bhi = reinterpret_cast<float*>(base + 2 * na);
+  *blo = reinterpret_cast<float*>(base + 2 * na + nb);
+}
+
 size_t tc_score_workspace_bytes(int G, int L, int S, int K) {
   return 2 * tc::al((size_t)G * L * K * 4) + 2 * tc::al((size_t)G * S * K * 4) + 4096;
 }

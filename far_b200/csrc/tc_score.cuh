@@ -10,4 +10,6 @@ int tc_score_lse_partials(const ScoreArgs& a, float2* rowpart, float2* colpart, 
                           int split_done, cudaStream_t st);
 int tc_match_conf(const ScoreArgs& a, const float* rowlse, const float* collse, float2* rowmax, float* colmax,
                   float* conf_out, float* ws, size_t ws_bytes, int split_done, cudaStream_t st);
+// Pointers of the dense [G][rows][K] hi/lo operand arrays inside a workspace filled by the passes above.
+void tc_score_operand_ptrs(const ScoreArgs& a, float* ws, float** ahi, float** alo, float** bhi, float** blo);
 }  // namespace far

@@ -172,8 +172,8 @@ def gen_vit8pt():
     ref.load_state_dict(sd, strict=True)
     g = np.random.default_rng(20240003)
     B = 2
-    images = torch.from_numpy(g.integers(0, 256, size=(B, 2, 3, 480, 640)).astype(np.float32))
-    intr = torch.tensor([[[400., 400., 320., 240.]] * 2, [[517.97, 517.97, 320., 240.]] * 2])
+    images = torch.from_numpy(g.integers(0, 256, size=(B, 2, 3, 448, 448)).astype(np.float32))  # exact 2x nearest resize
+    intr = torch.tensor([[[400., 400., 224., 224.]] * 2, [[517.97, 517.97, 224., 224.]] * 2])
     _, _, _, Rg, tg = synth.two_view_geometry(B, 16, seed=78)
     loftr_preds = torch.cat([Rg, tg[:, :, None]], dim=2).double()
     num_corr = torch.tensor([350, 12])
