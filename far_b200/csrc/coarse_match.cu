@@ -38,8 +38,8 @@ static MatchLayout match_layout(int N, int L, int S, int C = 256) {
     const int IT = score_tiles_i(L), JT = score_tiles_j(S);
     m.rowlse = off; off += al(R * 4);
     m.collse = off; off += al((size_t)N * S * 4);
-    m.rowmax = off; off += al((size_t)N * JT * L * 8);
-    m.colmax = off; off += al((size_t)N * IT * S * 4);
+    m.rowmax = off; off += al((size_t)N * 2 * JT * L * 8);  // 2x: the tcgen05 kernel emits two partials per tile
+    m.colmax = off; off += al((size_t)N * 2 * IT * S * 4);
     m.scratch = off; off += al(score_lse_scratch_floats(N, L, S) * 4);
     m.tcws_bytes = tc_score_workspace_bytes(N, L, S, C);
     m.tcws = off; off += al(m.tcws_bytes);
@@ -306,7 +306,8 @@ extern "C" int far_dual_softmax_match_select(const float* feat0, const float* fe
   float* csel = reinterpret_cast<float*>(base + m.csel);
   int* bcount = reinterpret_cast<int*>(base + m.bcount);
   long long* boff = reinterpret_cast<long long*>(base + m.boff);
-  match_decide_kernel<<<(unsigned)m.nblocks, kDecideThreads, 0, st>>>(p.rowmax, p.colmax, N, L, S, JT, IT, thr,
+  const int pj = used_tc ? 2 * JT : JT, pi = used_tc ? 2 * IT : IT;
+  match_decide_kernel<<<(unsigned)m.nblocks, kDecideThreads, 0, st>>>(p.rowmax, p.colmax, N, L, S, pj, pi, thr,
                                                                       border_rm, h0c, w0c, h1c, w1c, flag, jsel, csel,
                                                                       bcount);
   FAR_CHECK_LAUNCH();

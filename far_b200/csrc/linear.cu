@@ -152,6 +152,77 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
+// Vectorised variant for C = 128 * NV (NV <= 4): float4 loads, NV*4 values per lane, ~40 registers => full occupancy
+// so enough 512-byte row segments are in flight to cover HBM latency.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, const float* __restrict__ pre,
+                                                            int pre_rows, const float* __restrict__ g,
+                                                            const float* __restrict__ b, const float* __restrict__ res,
+                                                            float* __restrict__ y, int rows, float eps) {
+  constexpr int C = 128 * NV;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * C);
+  const float4* pr = pre ? reinterpret_cast<const float4*>(pre + (size_t)(warp % pre_rows) * C) : nullptr;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = __ldg(xr + lane + i * 32);
+    if (pr) {
+      const float4 q = __ldg(pr + lane + i * 32);
+      v[i].x += q.x; v[i].y += q.y; v[i].z += q.z; v[i].w += q.w;
+    }
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  const float4* r4 = res ? reinterpret_cast<const float4*>(res + (size_t)warp * C) : nullptr;
+  float4* y4 = reinterpret_cast<float4*>(y + (size_t)warp * C);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 gg = __ldg(g4 + lane + i * 32), bb = __ldg(b4 + lane + i * 32);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * gg.x + bb.x;
+    o.y = (v[i].y - mean) * rstd * gg.y + bb.y;
+    o.z = (v[i].z - mean) * rstd * gg.z + bb.z;
+    o.w = (v[i].w - mean) * rstd * gg.w + bb.w;
+    if (r4) {
+      const float4 rr = __ldg(r4 + lane + i * 32);
+      o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+    }
+    y4[lane + i * 32] = o;
+  }
+}
+
+static bool ln_vec_ok(const void* x, const void* pre, const void* g, const void* b, const void* res, const void* y, int C) {
+  auto a16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  return (C == 128 || C == 256 || C == 384 || C == 512) && a16(x) && a16(pre) && a16(g) && a16(b) && a16(res) && a16(y);
+}
+
+static void launch_layernorm(const float* x, const float* pre, int pre_rows, const float* g, const float* b,
+                             const float* res, float* y, int rows, int C, float eps, cudaStream_t st) {
+  const int wpb = 8;
+  const int grid = ceil_div(rows, wpb);
+  if (ln_vec_ok(x, pre, g, b, res, y, C)) {
+    switch (C / 128) {
+      case 1: layernorm_vec_kernel<1><<<grid, wpb * 32, 0, st>>>(x, pre, pre_rows, g, b, res, y, rows, eps); return;
+      case 2: layernorm_vec_kernel<2><<<grid, wpb * 32, 0, st>>>(x, pre, pre_rows, g, b, res, y, rows, eps); return;
+      case 3: layernorm_vec_kernel<3><<<grid, wpb * 32, 0, st>>>(x, pre, pre_rows, g, b, res, y, rows, eps); return;
+      default: layernorm_vec_kernel<4><<<grid, wpb * 32, 0, st>>>(x, pre, pre_rows, g, b, res, y, rows, eps); return;
+    }
+  }
+  layernorm_kernel<<<grid, wpb * 32, 0, st>>>(x, pre, pre_rows, g, b, res, y, rows, C, eps);
+}
+
 // ---------------------------------------------------------------------------------------------- pos-enc + flatten
 // out[n, hw, c] = feat[n,c,h,w] + pe[hw, c].  32x32 smem transpose when the input is NCHW (sw == 1);
 // straight coalesced copy when it is channels_last (sc == 1).
@@ -305,9 +376,7 @@ extern "C" int far_layernorm_pre(const float* x, const float* pre_add, int pre_r
                                  void* stream) {
   if (rows <= 0) return FAR_OK;
   FAR_REQUIRE(x && gamma && beta && y && C > 0 && C <= 1024 && (pre_add == nullptr || pre_rows > 0));
-  const int wpb = 8;
-  layernorm_kernel<<<ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(x, pre_add, pre_rows, gamma, beta,
-                                                                               residual, y, rows, C, eps);
+  launch_layernorm(x, pre_add, pre_rows, gamma, beta, residual, y, rows, C, eps, (cudaStream_t)stream);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }
@@ -316,9 +385,7 @@ extern "C" int far_layernorm(const float* x, const float* gamma, const float* be
                              int rows, int C, float eps, void* stream) {
   if (rows <= 0) return FAR_OK;
   FAR_REQUIRE(x && gamma && beta && y && C > 0 && C <= 1024);
-  const int wpb = 8;
-  layernorm_kernel<<<ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(x, nullptr, 1, gamma, beta, residual, y,
-                                                                               rows, C, eps);
+  launch_layernorm(x, nullptr, 1, gamma, beta, residual, y, rows, C, eps, (cudaStream_t)stream);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }

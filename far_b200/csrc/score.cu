@@ -64,11 +64,22 @@ __global__ void __launch_bounds__(kTileThreads, 2) score_lse_kernel(ScoreArgs a,
 
 // lse[g][x] = merge over tiles (fixed order) -> m + log(s)
 __global__ void lse_finalize_kernel(const float2* __restrict__ part, int tiles, int len, long long total,
-                                    float* __restrict__ lse) {
+                                    float* __restrict__ lse, int base2) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const long long g = idx / len;
   const int x = (int)(idx % len);
+  if (base2) {  // partials are (max, sum 2^(x - max)) of log2(e)-scaled scores (tcgen05 kernels)
+    float m = -INFINITY;
+    for (int tl = 0; tl < tiles; ++tl) m = fmaxf(m, part[((size_t)g * tiles + tl) * len + x].x);
+    float s = 0.f;
+    for (int tl = 0; tl < tiles; ++tl) {
+      const float2 p = part[((size_t)g * tiles + tl) * len + x];
+      if (p.x > -INFINITY) s += p.y * exp2f(p.x - m);
+    }
+    lse[idx] = (m + log2f(s)) * 0.6931471805599453f;
+    return;
+  }
   MS v = ms_init();
   for (int tl = 0; tl < tiles; ++tl) {
     const float2 p = part[((size_t)g * tiles + tl) * len + x];
@@ -81,9 +92,10 @@ int score_lse(const ScoreArgs& a, float* row_lse, float* col_lse, float* scratch
               size_t tcws_bytes, int* used_tc) {
   const int IT = score_tiles_i(a.L), JT = score_tiles_j(a.S);
   float2* rowpart = reinterpret_cast<float2*>(scratch);
-  float2* colpart = rowpart + (size_t)a.G * JT * a.L;
   const bool use_tc = tcws != nullptr && tcws_bytes >= tc_score_workspace_bytes(a.G, a.L, a.S, a.K) && tc_score_supported(a);
   if (used_tc) *used_tc = use_tc ? 1 : 0;
+  const int pj = use_tc ? 2 * JT : JT, pi = use_tc ? 2 * IT : IT;  // partial tiles per row / per column
+  float2* colpart = rowpart + (size_t)a.G * pj * a.L;
   if (use_tc) {
     int rc = tc_score_lse_partials(a, rowpart, colpart, tcws, tcws_bytes, 0, st);
     if (rc) return rc;
@@ -96,9 +108,9 @@ int score_lse(const ScoreArgs& a, float* row_lse, float* col_lse, float* scratch
     FAR_CHECK_LAUNCH();
   }
   const long long tr = (long long)a.G * a.L, tc = (long long)a.G * a.S;
-  lse_finalize_kernel<<<(unsigned)ceil_div_ll(tr, 256), 256, 0, st>>>(rowpart, JT, a.L, tr, row_lse);
+  lse_finalize_kernel<<<(unsigned)ceil_div_ll(tr, 256), 256, 0, st>>>(rowpart, pj, a.L, tr, row_lse, use_tc ? 1 : 0);
   FAR_CHECK_LAUNCH();
-  lse_finalize_kernel<<<(unsigned)ceil_div_ll(tc, 256), 256, 0, st>>>(colpart, IT, a.S, tc, col_lse);
+  lse_finalize_kernel<<<(unsigned)ceil_div_ll(tc, 256), 256, 0, st>>>(colpart, pi, a.S, tc, col_lse, use_tc ? 1 : 0);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }

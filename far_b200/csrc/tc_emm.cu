@@ -53,7 +53,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void epi_bar2() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+constexpr int E_THREADS = 64 + 256;         // producer warp, MMA warp, 8 softmax warps
+__device__ __forceinline__ void epi_bar2() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+__device__ __forceinline__ float ex2a(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct EmmTcArgs {
   int G, H, N, d;            // groups, heads per batch, tokens, head dim
@@ -66,7 +72,7 @@ struct EmmTcArgs {
   float* Fpart;              // [G][IT][dv*dv]
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(E_THREADS, 1)
 tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant__ CUtensorMap mapQlo,
                  const __grid_constant__ CUtensorMap mapKhi, const __grid_constant__ CUtensorMap mapKlo,
                  const __grid_constant__ CUtensorMap mapVhi, const __grid_constant__ CUtensorMap mapVlo, EmmTcArgs p) {
@@ -95,7 +101,7 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   const int JT = (p.N + EBJ - 1) / EBJ;
 
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(p_empty, 1); mbar_init(t_full, 1);
+    mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(p_empty, 1); mbar_init(t_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -183,17 +189,20 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       umma_commit(t_full);
     }
   } else {
-    // ===================== softmax / epilogue warps (thread = query row) =====================
+    // ===================== softmax / epilogue: 8 warps, thread = (query row, 32-key half of the j-tile) =========
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
-    const int et = (warp - 2) * 32 + lane;
+    const int et = (warp - 2) * 32 + lane;  // 0..255
     const int grow = i0 + row;
     const bool rvalid = grow < p.N;
-    const float rl = rvalid ? p.rowlse[(size_t)g * p.N + grow] : 0.f;
+    constexpr float kL2e = 1.4426950408889634f;
+    const float rl2 = rvalid ? p.rowlse[(size_t)g * p.N + grow] * kL2e : 0.f;
+    const float scale2x2 = 2.f * p.scale * kL2e;  // P = exp(2 s - rowlse - collse) = 2^(2 s log2e - rl2 - cl2)
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     for (int jt = 0; jt < JT; ++jt) {
       const int j0 = jt * EBJ;
-      if (et < EBJ) cls[et] = (j0 + et < p.N) ? p.collse[(size_t)g * p.N + j0 + et] : 0.f;
+      if (et < EBJ) cls[et] = (j0 + et < p.N) ? p.collse[(size_t)g * p.N + j0 + et] * kL2e : 0.f;
       epi_bar2();
       mbar_wait(s_full, (uint32_t)(jt & 1));
       tc_fence_after();
@@ -201,22 +210,21 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         mbar_wait(p_empty, (uint32_t)((jt - 1) & 1));
         tc_fence_after();
       }
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t a[32], b[32];
-        tmem_ld32(tS_main + lane_off + (uint32_t)(c * 32), a);
-        tmem_ld32(tS_cross + lane_off + (uint32_t)(c * 32), b);
+        tmem_ld32(tS_main + lane_off + (uint32_t)(half * 32), a);
+        tmem_ld32(tS_cross + lane_off + (uint32_t)(half * 32), b);
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          const float x = (__uint_as_float(a[e]) + __uint_as_float(b[e])) * p.scale;
-          const bool ok = rvalid && (j0 + c * 32 + e) < p.N;
-          const float pv = ok ? expf((x - rl) + (x - cls[c * 32 + e])) : 0.f;
+          const float x = __uint_as_float(a[e]) + __uint_as_float(b[e]);
+          const bool ok = rvalid && (j0 + half * 32 + e) < p.N;
+          const float pv = ok ? ex2a(fmaf(x, scale2x2, -(rl2 + cls[half * 32 + e]))) : 0.f;
           const uint32_t h = __float_as_uint(pv) & 0xFFFFE000u;
           a[e] = h;                                            // hi
           b[e] = __float_as_uint(pv - __uint_as_float(h));     // lo (exact)
         }
-        tmem_st32(tP_hi + lane_off + (uint32_t)(c * 32), a);
-        tmem_st32(tP_lo + lane_off + (uint32_t)(c * 32), b);
+        tmem_st32(tP_hi + lane_off + (uint32_t)(half * 32), a);
+        tmem_st32(tP_lo + lane_off + (uint32_t)(half * 32), b);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -228,7 +236,7 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     mbar_wait(t_full, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < EDVP / 32; ++c) {
+    for (int c = half; c < EDVP / 32; c += 2) {
       uint32_t a[32], b[32];
       tmem_ld32(tT_main + lane_off + (uint32_t)(c * 32), a);
       tmem_ld32(tT_cross + lane_off + (uint32_t)(c * 32), b);
@@ -239,7 +247,7 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       const int b = g / p.H, h = g % p.H, dv = p.d + 6;
       const float* vb = p.v + (size_t)b * p.sb + (size_t)h * p.sh;
       const float* pb = p.pos + (size_t)(p.Bpos == 1 ? 0 : b) * p.N * 6;
-      for (int idx = et; idx < BM * EDVP; idx += 128) {
+      for (int idx = et; idx < BM * EDVP; idx += 256) {
         const int r = idx / EDVP, c = idx % EDVP, tok = i0 + r;
         float val = 0.f;
         if (tok < p.N) {
@@ -250,7 +258,7 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       }
       epi_bar2();
       float* out = p.Fpart + ((size_t)g * IT + it) * dv * dv;
-      for (int idx = et; idx < dv * dv; idx += 128) {
+      for (int idx = et; idx < dv * dv; idx += 256) {
         const int aa = idx / dv, cc = idx % dv;
         float s = 0.f;
 #pragma unroll 8
@@ -348,7 +356,7 @@ int tc_emm_pv(const float* qhi, const float* qlo, const float* khi, const float*
     attr = true;
   }
   EmmTcArgs p{G, H, N, d, scale, rowlse, collse, v, sb, sh, ldv, pos, Bpos, Fpart};
-  tc_emm_pv_kernel<<<dim3(ceil_div(N, BM), G), NUM_THREADS, EMM_SMEM, st>>>(mQhi, mQlo, mKhi, mKlo, mVhi, mVlo, p);
+  tc_emm_pv_kernel<<<dim3(ceil_div(N, BM), G), E_THREADS, EMM_SMEM, st>>>(mQhi, mQlo, mKhi, mKlo, mVhi, mVlo, p);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }

@@ -15,43 +15,50 @@ namespace far {
 namespace tc {
 
 constexpr int MODE_LSE = 0, MODE_CONF = 1;
-constexpr int SPITCH = 33;
-constexpr size_t SCORE_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + 256 + (size_t)BM * SPITCH * 4 + 4 * 32 * 8 + BN * 4;
+constexpr int S_STAGES = 2;                 // 2 x 64 KiB operand ring leaves room for a full-tile transpose buffer
+constexpr int S_THREADS = 64 + 256;         // producer warp, MMA warp, 8 epilogue warps
+constexpr int SPITCH = BN + 1;              // 129: conflict-free row writes and column reads
+constexpr size_t SCORE_SMEM = 1024 + (size_t)S_STAGES * STAGE_BYTES + 256 + (size_t)BM * SPITCH * 4 + BN * 4;
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
 struct ScoreTcArgs {
   int G, H, L, S, K;       // groups (= nb * H), heads per batch, rows of A, rows of B, contraction
-  float scale;
-  // MODE_LSE outputs
-  float2* rowpart;         // [(g*JT + jt)*L + i] (m, s)
-  float2* colpart;         // [(g*IT + it)*S + j]
+  float scale2;            // scale * log2(e): scores are handled in the base-2 domain (one MUFU.EX2 per exponential)
+  // MODE_LSE outputs (base-2 (max, sum 2^(x-max)) partials; 2 partial "tiles" per 128-wide tile in each direction)
+  float2* rowpart;         // [(g*2JT + 2jt+half)*L + i]
+  float2* colpart;         // [(g*2IT + 2it+half)*S + j]
   // MODE_CONF inputs / outputs
-  const float* rowlse;     // [G][L]
+  const float* rowlse;     // [G][L] natural log
   const float* collse;     // [G][S]
-  float2* rowmax;          // [(g*JT + jt)*L + i] (conf, bits(j))
-  float* colmax;           // [(g*IT + it)*S + j]
+  float2* rowmax;          // [(g*2JT + 2jt+half)*L + i] (conf, bits(j))
+  float* colmax;           // [(g*2IT + 2it+half)*S + j]
   float* conf_out;         // optional [G][L][S]
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(S_THREADS, 1)
 tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, ScoreTcArgs p) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = base + S_STAGES * STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * S_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * S_STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S_STAGES + 4);
   unsigned char* gen = smem_dyn + (bar_base + 256 - raw);  // generic pointer to the epilogue scratch
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - raw));
   float(*scr)[SPITCH] = reinterpret_cast<float(*)[SPITCH]>(gen);
-  float2(*part)[32] = reinterpret_cast<float2(*)[32]>(gen + (size_t)BM * SPITCH * 4);
-  float* cls = reinterpret_cast<float*>(gen + (size_t)BM * SPITCH * 4 + 4 * 32 * 8);
+  float* cls2 = reinterpret_cast<float*>(gen + (size_t)BM * SPITCH * 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int IT = (p.L + BM - 1) / BM, JT = (p.S + BN - 1) / BN;
@@ -59,8 +66,8 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
   const int kblocks = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < S_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -88,7 +95,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
           tma_load_4d(sbase + 1 * TILE_BYTES, &mapAlo, full_bar(stage), kb * BK, it * BM, g0, g1);
           tma_load_4d(sbase + 2 * TILE_BYTES, &mapBhi, full_bar(stage), kb * BK, jt * BN, g0, g1);
           tma_load_4d(sbase + 3 * TILE_BYTES, &mapBlo, full_bar(stage), kb * BK, jt * BN, g0, g1);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == S_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -119,18 +126,19 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
             umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == S_STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
-    // ===================== epilogue: 128 threads, thread = tile row =====================
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;       // row inside the tile
-    const int et = (warp - 2) * 32 + lane;     // 0..127 dense epilogue thread id (column-phase mapping)
-    const int ce = et & 31, cq = et >> 5;      // column-phase: column ce of the chunk, rows [32*cq, 32*cq + 32)
+    // ===================== epilogue: 8 warps; thread = (tile row, 64-column half) =====================
+    const int quarter = warp & 3;              // TMEM lane window
+    const int half = (warp - 2) >> 2;          // which 64 columns of the 128-wide tile
+    const int row = quarter * 32 + lane;
+    const int et = (warp - 2) * 32 + lane;     // 0..255
+    const int ccol = et & 127, crh = et >> 7;  // column phase: column ccol, rows [64*crh, 64*crh + 64)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -138,105 +146,87 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       const int i0 = it * BM, j0 = jt * BN;
       const int grow = i0 + row;
       const bool rvalid = grow < p.L;
+      float rl2 = 0.f;
+      if (MODE == MODE_CONF) {
+        rl2 = rvalid ? p.rowlse[(size_t)g * p.L + grow] * kLog2e : 0.f;
+        if (et < BN) cls2[et] = (j0 + et < p.S) ? p.collse[(size_t)g * p.S + j0 + et] * kLog2e : 0.f;
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      float rl = 0.f;
-      if (MODE == MODE_CONF) {
-        rl = rvalid ? p.rowlse[(size_t)g * p.L + grow] : 0.f;
-        const int c = j0 + et;
-        cls[et] = (c < p.S) ? p.collse[(size_t)g * p.S + c] : 0.f;
-        epi_bar();
-      }
-      float m_r = -INFINITY, s_r = 0.f;   // MODE_LSE row accumulators
-      float bv = -1.f;                     // MODE_CONF row (max, argmax)
-      int bj = 0x7fffffff;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      float x[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32], vs[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + half * 64 + c * 32);
         tmem_ld32(taddr, v);
         tmem_ld32(taddr + (uint32_t)BN, vs);
-        const int col0 = j0 + c * 32;
-        float x[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) x[e] = (__uint_as_float(v[e]) + __uint_as_float(vs[e])) * p.scale;
-        if (MODE == MODE_LSE) {
-          float cm = -INFINITY;
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (col0 + e < p.S) cm = fmaxf(cm, x[e]);
-          if (rvalid && cm > -INFINITY) {
-            const float nm = fmaxf(m_r, cm);
-            float acc_s = (m_r == -INFINITY) ? 0.f : s_r * expf(m_r - nm);
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (col0 + e < p.S) acc_s += expf(x[e] - nm);
-            m_r = nm;
-            s_r = acc_s;
-          }
-#pragma unroll
-          for (int e = 0; e < 32; ++e) scr[row][e] = rvalid ? x[e] : -INFINITY;
-          epi_bar();
-          {  // column phase: (max, sumexp) over 32 rows of one column
-            float pm = -INFINITY;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) pm = fmaxf(pm, scr[cq * 32 + r][ce]);
-            float ps = 0.f;
-            if (pm > -INFINITY) {
-#pragma unroll 8
-              for (int r = 0; r < 32; ++r) ps += expf(scr[cq * 32 + r][ce] - pm);  // exp(-inf) = 0 for masked rows
-            }
-            part[cq][ce] = make_float2(pm, ps);
-          }
-          epi_bar();
-          if (et < 32) {
-            MS a = ms_init();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) a = ms_merge(a, MS{part[q][et].x, part[q][et].y});
-            const int col = col0 + et;
-            if (col < p.S) p.colpart[((size_t)g * IT + it) * p.S + col] = make_float2(a.m, a.s);
-          }
-          epi_bar();
-        } else {
-          // conf = softmax(sim, 1) * softmax(sim, 2)
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int col = col0 + e;
-            const bool ok = rvalid && col < p.S;
-            x[e] = ok ? expf(x[e] - rl) * expf(x[e] - cls[c * 32 + e]) : -1.f;
-            if (x[e] > bv) { bv = x[e]; bj = col; }   // ascending columns, strict > keeps the lowest j on ties
-          }
-          if (p.conf_out != nullptr && rvalid) {
-            float* dst = p.conf_out + ((size_t)g * p.L + grow) * p.S + col0;
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (col0 + e < p.S) dst[e] = x[e];
-          }
-#pragma unroll
-          for (int e = 0; e < 32; ++e) scr[row][e] = x[e];
-          epi_bar();
-          {
-            float pm = -1.f;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) pm = fmaxf(pm, scr[cq * 32 + r][ce]);
-            part[cq][ce] = make_float2(pm, 0.f);
-          }
-          epi_bar();
-          if (et < 32) {
-            float a = fmaxf(fmaxf(part[0][et].x, part[1][et].x), fmaxf(part[2][et].x, part[3][et].x));
-            const int col = col0 + et;
-            if (col < p.S) p.colmax[((size_t)g * IT + it) * p.S + col] = a;
-          }
-          epi_bar();
-        }
+        for (int e = 0; e < 32; ++e) x[c * 32 + e] = (__uint_as_float(v[e]) + __uint_as_float(vs[e])) * p.scale2;
       }
-      if (rvalid) {
-        if (MODE == MODE_LSE) p.rowpart[((size_t)g * JT + jt) * p.L + grow] = make_float2(m_r, s_r);
-        else p.rowmax[((size_t)g * JT + jt) * p.L + grow] = make_float2(bv, __int_as_float(bj));
-      }
+      // the accumulator is in registers now: hand the TMEM buffer back to the MMA warp early
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      const int col0 = j0 + half * 64;
+      if (MODE == MODE_LSE) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 64; ++e) {
+          if (!(rvalid && col0 + e < p.S)) x[e] = -INFINITY;
+          m = fmaxf(m, x[e]);
+        }
+        float sum = 0.f;
+        if (m > -INFINITY) {
+#pragma unroll
+          for (int e = 0; e < 64; ++e) sum += ex2(x[e] - m);  // 2^(-inf) = 0 for masked entries
+        }
+        if (rvalid) p.rowpart[((size_t)g * 2 * JT + 2 * jt + half) * p.L + grow] = make_float2(m, sum);
+#pragma unroll
+        for (int e = 0; e < 64; ++e) scr[row][half * 64 + e] = x[e];
+        epi_bar();
+        {
+          float cm = -INFINITY;
+#pragma unroll 16
+          for (int r = 0; r < 64; ++r) cm = fmaxf(cm, scr[crh * 64 + r][ccol]);
+          float cs = 0.f;
+          if (cm > -INFINITY) {
+#pragma unroll 16
+            for (int r = 0; r < 64; ++r) cs += ex2(scr[crh * 64 + r][ccol] - cm);
+          }
+          const int col = j0 + ccol;
+          if (col < p.S) p.colpart[((size_t)g * 2 * IT + 2 * it + crh) * p.S + col] = make_float2(cm, cs);
+        }
+        epi_bar();
+      } else {
+        epi_bar();  // cls2 staged
+        float bv = -1.f;
+        int bj = 0x7fffffff;
+#pragma unroll
+        for (int e = 0; e < 64; ++e) {
+          const int col = col0 + e;
+          const bool ok = rvalid && col < p.S;
+          x[e] = ok ? ex2(x[e] - rl2) * ex2(x[e] - cls2[half * 64 + e]) : -1.f;   // softmax(sim,1) * softmax(sim,2)
+          if (x[e] > bv) { bv = x[e]; bj = col; }   // ascending columns, strict > keeps the lowest j on ties
+        }
+        if (rvalid) p.rowmax[((size_t)g * 2 * JT + 2 * jt + half) * p.L + grow] = make_float2(bv, __int_as_float(bj));
+        if (p.conf_out != nullptr && rvalid) {
+          float* dst = p.conf_out + ((size_t)g * p.L + grow) * p.S + col0;
+#pragma unroll
+          for (int e = 0; e < 64; ++e)
+            if (col0 + e < p.S) dst[e] = x[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 64; ++e) scr[row][half * 64 + e] = x[e];
+        epi_bar();
+        {
+          float cm = -1.f;
+#pragma unroll 16
+          for (int r = 0; r < 64; ++r) cm = fmaxf(cm, scr[crh * 64 + r][ccol]);
+          const int col = j0 + ccol;
+          if (col < p.S) p.colmax[((size_t)g * 2 * IT + 2 * it + crh) * p.S + col] = cm;
+        }
+        epi_bar();
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -330,11 +320,11 @@ int tc_score_lse_partials(const ScoreArgs& a, float2* rowpart, float2* colpart, 
   if (rc) return rc;
   set_attr_once();
   ScoreTcArgs p{};
-  p.G = a.G; p.H = a.H; p.L = a.L; p.S = a.S; p.K = a.K; p.scale = a.scale;
+  p.G = a.G; p.H = a.H; p.L = a.L; p.S = a.S; p.K = a.K; p.scale2 = a.scale * kLog2e;
   p.rowpart = rowpart; p.colpart = colpart;
   const int tiles = a.G * ceil_div(a.L, BM) * ceil_div(a.S, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  tc_score_kernel<MODE_LSE><<<grid, NUM_THREADS, SCORE_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  tc_score_kernel<MODE_LSE><<<grid, S_THREADS, SCORE_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }
@@ -348,11 +338,11 @@ int tc_match_conf(const ScoreArgs& a, const float* rowlse, const float* collse, 
   if (rc) return rc;
   set_attr_once();
   ScoreTcArgs p{};
-  p.G = a.G; p.H = a.H; p.L = a.L; p.S = a.S; p.K = a.K; p.scale = a.scale;
+  p.G = a.G; p.H = a.H; p.L = a.L; p.S = a.S; p.K = a.K; p.scale2 = a.scale * kLog2e;
   p.rowlse = rowlse; p.collse = collse; p.rowmax = rowmax; p.colmax = colmax; p.conf_out = conf_out;
   const int tiles = a.G * ceil_div(a.L, BM) * ceil_div(a.S, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  tc_score_kernel<MODE_CONF><<<grid, NUM_THREADS, SCORE_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  tc_score_kernel<MODE_CONF><<<grid, S_THREADS, SCORE_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }
