@@ -156,6 +156,150 @@ __global__ void __launch_bounds__(256) la_small_kernel(const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// D = 32 fast path: one CTA covers ALL heads of a token tile, so every global access is a full contiguous C-float row
+// (1 KB at C = 256) instead of eight 128-byte head slices read by eight different CTAs; 16 float4 loads in flight per
+// thread.  Warp w owns head w.  Same partial layout as la_reduce_kernel, so both apply kernels can consume it.
+constexpr int LA2_T = 32;  // tokens per shared-memory tile
+
+template <int H>
+__global__ void __launch_bounds__(32 * H) la_reduce_allheads_kernel(const float* __restrict__ k, int ldk,
+                                                                    const float* __restrict__ v, int ldv, int S,
+                                                                    int applied, int chunk, float* __restrict__ ws) {
+  constexpr int D = 32, C = H * D, NT = 32 * H;
+  extern __shared__ __align__(16) float la_sm[];
+  float(*Ks)[C] = reinterpret_cast<float(*)[C]>(la_sm);
+  float(*Vs)[C] = reinterpret_cast<float(*)[C]>(la_sm + LA2_T * C);
+  const int n = blockIdx.x, z = blockIdx.y, t = threadIdx.x, h = t >> 5, lane = t & 31;
+  const int dq = lane >> 3, eq = lane & 7;  // this lane: d in [8 dq, 8 dq + 8), e in [4 eq, 4 eq + 4)
+  const int s_beg = z * chunk, s_end = min(S, s_beg + chunk);
+  const float fS = (float)S;
+  float acc[8][4];
+  float ksum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    ksum[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  }
+  const float* kb = k + (size_t)n * S * ldk;
+  const float* vb = v + (size_t)n * S * ldv;
+  for (int s0 = s_beg; s0 < s_end; s0 += LA2_T) {
+    const int cnt = min(LA2_T, s_end - s0);
+    for (int idx = t; idx < LA2_T * C / 4; idx += NT) {
+      const int r = idx / (C / 4), c4 = idx % (C / 4);
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (r < cnt) {
+        kv = __ldg(reinterpret_cast<const float4*>(kb + (size_t)(s0 + r) * ldk) + c4);
+        vv = __ldg(reinterpret_cast<const float4*>(vb + (size_t)(s0 + r) * ldv) + c4);
+        kv.x = fmap(kv.x, applied); kv.y = fmap(kv.y, applied); kv.z = fmap(kv.z, applied); kv.w = fmap(kv.w, applied);
+        vv.x /= fS; vv.y /= fS; vv.z /= fS; vv.w /= fS;  // values / v_length (:44)
+      }
+      reinterpret_cast<float4*>(&Ks[r][0])[c4] = kv;
+      reinterpret_cast<float4*>(&Vs[r][0])[c4] = vv;
+    }
+    __syncthreads();
+    for (int r = 0; r < cnt; ++r) {
+      const float4 k0 = *reinterpret_cast<const float4*>(&Ks[r][h * D + dq * 8]);
+      const float4 k1 = *reinterpret_cast<const float4*>(&Ks[r][h * D + dq * 8 + 4]);
+      const float4 v0 = *reinterpret_cast<const float4*>(&Vs[r][h * D + eq * 4]);
+      const float kk[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+      const float vv[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ksum[i] += kk[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(kk[i], vv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+  float* out = ws + ((size_t)(n * H + h) * gridDim.y + z) * (D * D + D);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    *reinterpret_cast<float4*>(&out[(dq * 8 + i) * D + eq * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if (eq == 0) out[D * D + dq * 8 + i] = ksum[i];
+  }
+}
+
+template <int H>
+__global__ void __launch_bounds__(32 * H) la_apply_allheads_kernel(const float* __restrict__ q, int ldq,
+                                                                   float* __restrict__ out, int ldo, int L, int S,
+                                                                   int applied, int splits, float eps,
+                                                                   const float* __restrict__ ws) {
+  constexpr int D = 32, C = H * D, NT = 32 * H, KVP = D * (D + 1);
+  extern __shared__ __align__(16) float la_sm[];
+  float(*Qs)[C] = reinterpret_cast<float(*)[C]>(la_sm);        // [LA2_T][C]
+  float* KV = la_sm + LA2_T * C;                                 // [H][D][D+1]
+  float* Ksum = KV + H * KVP;                                    // [H][D]
+  const int n = blockIdx.x, l0 = blockIdx.y * LA2_T, t = threadIdx.x, h = t >> 5, lane = t & 31;
+  const int cnt = min(LA2_T, L - l0);
+  for (int idx = t; idx < H * (D * D + D); idx += NT) {
+    const int hh = idx / (D * D + D), e = idx % (D * D + D);
+    float sacc = 0.f;
+    for (int zz = 0; zz < splits; ++zz) sacc += ws[((size_t)(n * H + hh) * splits + zz) * (D * D + D) + e];
+    if (e < D * D) KV[hh * KVP + (e / D) * (D + 1) + e % D] = sacc; else Ksum[hh * D + e - D * D] = sacc;
+  }
+  const float* qb = q + ((size_t)n * L + l0) * ldq;
+  for (int idx = t; idx < LA2_T * C / 4; idx += NT) {
+    const int r = idx / (C / 4), c4 = idx % (C / 4);
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < cnt) {
+      qv = __ldg(reinterpret_cast<const float4*>(qb + (size_t)r * ldq) + c4);
+      qv.x = fmap(qv.x, applied); qv.y = fmap(qv.y, applied); qv.z = fmap(qv.z, applied); qv.w = fmap(qv.w, applied);
+    }
+    reinterpret_cast<float4*>(&Qs[r][0])[c4] = qv;
+  }
+  __syncthreads();
+  const float* kvh = KV + h * KVP;
+  const float* ksh = Ksum + h * D;
+  for (int r0 = 0; r0 < cnt; r0 += 4) {  // 4 tokens at a time: KV[d][lane] is loaded once for all four
+    float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int d4 = 0; d4 < D; d4 += 4) {
+      float4 qq[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qq[i] = *reinterpret_cast<const float4*>(&Qs[min(r0 + i, LA2_T - 1)][h * D + d4]);
+      const float4 ks = *reinterpret_cast<const float4*>(&ksh[d4]);
+      const float kv0 = kvh[(d4 + 0) * (D + 1) + lane], kv1 = kvh[(d4 + 1) * (D + 1) + lane],
+                  kv2 = kvh[(d4 + 2) * (D + 1) + lane], kv3 = kvh[(d4 + 3) * (D + 1) + lane];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        num[i] = fmaf(qq[i].x, kv0, num[i]); num[i] = fmaf(qq[i].y, kv1, num[i]);
+        num[i] = fmaf(qq[i].z, kv2, num[i]); num[i] = fmaf(qq[i].w, kv3, num[i]);
+        den[i] = fmaf(qq[i].x, ks.x, den[i]); den[i] = fmaf(qq[i].y, ks.y, den[i]);
+        den[i] = fmaf(qq[i].z, ks.z, den[i]); den[i] = fmaf(qq[i].w, ks.w, den[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (r0 + i < cnt)
+        out[((size_t)n * L + l0 + r0 + i) * ldo + h * D + lane] = num[i] * (1.f / (den[i] + eps)) * (float)S;
+  }
+}
+
+static inline bool ptr_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// sum of the per-split partials (fixed order) -> one [D*D + D] record per (n, h)
+__global__ void la_partial_sum_kernel(const float* __restrict__ ws, int splits, int rec, long long total,
+                                      float* __restrict__ outp) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long nh = idx / rec;
+  const int e = (int)(idx % rec);
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += ws[((size_t)nh * splits + z) * rec + e];
+  outp[idx] = s;
+}
+
+static int la_splits_allheads(int N, int S) {
+  int s = (3 * kNumSMs + N - 1) / N;
+  const int maxs = ceil_div(S, 4 * LA2_T);
+  if (s > maxs) s = maxs;
+  if (s < 1) s = 1;
+  return s;
+}
+
 static int la_splits(int N, int S, int H) {
   const long long base = (long long)N * H;
   int s = (int)((4LL * kNumSMs + base - 1) / base);
@@ -164,6 +308,8 @@ static int la_splits(int N, int S, int H) {
   if (s < 1) s = 1;
   return s;
 }
+
+size_t linear_attention_ws_bytes(int N, int S, int H, int D);
 
 int linear_attention_dispatch(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out,
                               int ldo, int N, int L, int S, int H, int D, float eps, int applied, float* workspace,
@@ -177,9 +323,31 @@ int linear_attention_dispatch(const float* q, int ldq, const float* k, int ldk, 
     FAR_CHECK_LAUNCH();
     return FAR_OK;
   }
+  if (workspace == nullptr || workspace_bytes < linear_attention_ws_bytes(N, S, H, D) - 256) return FAR_ERR_WORKSPACE;
   const int splits = la_splits(N, S, H);
-  const size_t need = (size_t)N * H * splits * (D * D + D) * sizeof(float);
-  if (workspace == nullptr || workspace_bytes < need) return FAR_ERR_WORKSPACE;
+  if (D == 32 && H == 8 && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ptr_al16(q) && ptr_al16(k) && ptr_al16(v)) {
+    constexpr int HH = 8, CC = HH * 32;
+    const int sp2 = la_splits_allheads(N, S);
+    const int chunk2 = ceil_div(ceil_div(S, sp2), LA2_T) * LA2_T;
+    const int rec = 32 * 32 + 32;
+    float* summed = workspace + (size_t)N * HH * sp2 * rec;
+    const size_t sm1 = (size_t)2 * LA2_T * CC * 4, sm2 = ((size_t)LA2_T * CC + HH * (32 * 33) + HH * 32) * 4;
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(la_reduce_allheads_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+      cudaFuncSetAttribute(la_apply_allheads_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      attr = true;
+    }
+    la_reduce_allheads_kernel<HH><<<dim3(N, sp2), 32 * HH, sm1, st>>>(k, ldk, v, ldv, S, applied, chunk2, workspace);
+    FAR_CHECK_LAUNCH();
+    const long long tot = (long long)N * HH * rec;
+    la_partial_sum_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(workspace, sp2, rec, tot, summed);
+    FAR_CHECK_LAUNCH();
+    la_apply_allheads_kernel<HH><<<dim3(N, ceil_div(L, LA2_T)), 32 * HH, sm2, st>>>(q, ldq, out, ldo, L, S, applied, 1, eps,
+                                                                                    summed);
+    FAR_CHECK_LAUNCH();
+    return FAR_OK;
+  }
   const int chunk = ceil_div(ceil_div(S, splits), LA_TOK) * LA_TOK;
   dim3 g1(N * H, splits), g2(N * H, ceil_div(L, LA_TOK));
   if (D == 16) {
@@ -196,7 +364,8 @@ int linear_attention_dispatch(const float* q, int ldq, const float* k, int ldk, 
 }
 
 size_t linear_attention_ws_bytes(int N, int S, int H, int D) {
-  return (size_t)N * H * la_splits(N, S, H) * (D * D + D) * sizeof(float) + 256;
+  const int a = la_splits(N, S, H), b = la_splits_allheads(N, S);
+  return (size_t)N * H * ((a > b ? a : b) + 1) * (D * D + D) * sizeof(float) + 256;
 }
 
 }  // namespace far

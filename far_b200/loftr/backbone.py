@@ -58,8 +58,10 @@ class ResNetFPN_8_2(nn.Module):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
 
+    memory_format = torch.channels_last
+
     def forward(self, x):
-        x = x.contiguous(memory_format=torch.channels_last)
+        x = x.contiguous(memory_format=self.memory_format)
         x0 = self.relu(self.bn1(self.conv1(x)))
         x1 = self.layer1(x0)
         x2 = self.layer2(x1)
@@ -70,6 +72,36 @@ class ResNetFPN_8_2(nn.Module):
         x2_up = F.interpolate(x2_out, scale_factor=2., mode='bilinear', align_corners=True)
         x1_out = self.layer1_outconv2(self.layer1_outconv(x1) + x2_up)
         return [x3_out, x1_out]
+
+
+def fold_batchnorm(module):
+    """Eval-time rewrite: fold every (Conv2d -> BatchNorm2d) pair into the convolution (w' = w * g/sqrt(var+eps),
+    b' = beta - mean * g/sqrt(var+eps)).  Legal because BN is in eval mode on the whole path (SURVEY.md 8f rank 1);
+    removes one elementwise pass per conv.  Returns a deep copy; the original keeps the checkpoint's parameter names."""
+    import copy
+    m = copy.deepcopy(module).eval()
+
+    def fuse(conv, bn):
+        w = conv.weight
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        fused = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, bias=True)
+        fused = fused.to(w.device, w.dtype)
+        with torch.no_grad():
+            fused.weight.copy_(w * scale[:, None, None, None])
+            b0 = conv.bias if conv.bias is not None else torch.zeros_like(bn.running_mean)
+            fused.bias.copy_((b0 - bn.running_mean) * scale + bn.bias)
+        return fused
+
+    m.conv1, m.bn1 = fuse(m.conv1, m.bn1), nn.Identity()
+    for layer in (m.layer1, m.layer2, m.layer3):
+        for blk in layer:
+            blk.conv1, blk.bn1 = fuse(blk.conv1, blk.bn1), nn.Identity()
+            blk.conv2, blk.bn2 = fuse(blk.conv2, blk.bn2), nn.Identity()
+            if blk.downsample is not None:
+                blk.downsample = nn.Sequential(fuse(blk.downsample[0], blk.downsample[1]))
+    for seq in (m.layer2_outconv2, m.layer1_outconv2):
+        seq[0], seq[1] = fuse(seq[0], seq[1]), nn.Identity()
+    return m
 
 
 def build_backbone(config):
