@@ -126,11 +126,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     uint32_t acc_phase = 0;
     const int actc = p.act_cols < 0 ? p.N : p.act_cols;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+    float* stg = reinterpret_cast<float*>(smem_dyn + (bar_base + 256 - raw)) + (warp - 2) * (32 * 33);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32], vs[32];
@@ -138,27 +138,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         tmem_ld32(taddr, v);
         tmem_ld32(taddr + (uint32_t)BN, vs);
         const int col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N) {
-          float* dst = p.C + (size_t)row * p.ldc + col0;
+        // bias / activation on this thread's row segment, then a 32x32 transpose through shared memory so that every
+        // global store instruction writes four full 128-byte row segments (row-per-thread 16-byte stores measured
+        // ~20 us per tile: partial-sector writes).
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float o[4];
+        for (int e = 0; e < 32; ++e) {
+          const int col = col0 + e;
+          float t = __uint_as_float(v[e]) + __uint_as_float(vs[e]);
+          if (col < p.N) {
+            if (p.bias) t += __ldg(p.bias + col);
+            if (col < actc) t = apply_act(t, p.act);
+          }
+          stg[lane * 33 + e] = t;
+        }
+        __syncwarp();
+        const int c4 = lane & 7;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int col = col0 + j + e;
-              float t = __uint_as_float(v[j + e]) + __uint_as_float(vs[j + e]);
-              if (col < p.N) {
-                if (p.bias) t += __ldg(p.bias + col);
-                if (col < actc) t = apply_act(t, p.act);
-              }
-              o[e] = t;
-            }
-            if (vec_ok && col0 + j + 3 < p.N) {
-              *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3);
+          const int grow = m0 + quarter * 32 + r;
+          const int col = col0 + c4 * 4;
+          const float* src = stg + r * 33 + c4 * 4;
+          if (grow < p.M && col < p.N) {
+            float* dst = p.C + (size_t)grow * p.ldc + col;
+            if (vec_ok && col + 3 < p.N) {
+              *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[1], src[2], src[3]);
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                if (col0 + j + e < p.N) dst[j + e] = o[e];
+                if (col + e < p.N) dst[e] = src[e];
             }
           }
         }

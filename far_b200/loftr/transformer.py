@@ -266,7 +266,7 @@ class LocalFeatureTransformerRegressor(nn.Module):
         tail = torch.cat([pred_reg_6d, loftr_preds.float()], dim=-1)              # [B, 9 + pose_size_in]
         m0 = self.moe_predictor[0]
         # moe_predictor.0 on cat([features, pred, solver]): two K-segments, no [B,35862] concat (transformer.py:458-459)
-        hid = ops.linear_cat_tail(features, tail, m0.weight, m0.bias, ACT_RELU)
+        hid = ops.linear_cat_tail(features, tail, m0, ACT_RELU)
         hid = ops.linear(hid, self.moe_predictor[2].weight, self.moe_predictor[2].bias, ACT_RELU)
         pred_RT_wt = ops.linear(hid, self.moe_predictor[4].weight, self.moe_predictor[4].bias, ACT_SIGMOID)
         if rc['use_2wt'] and not rc['use_5050_weight']:

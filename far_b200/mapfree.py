@@ -48,7 +48,7 @@ class RegressionHead(nn.Module):
         ratio = torch.linalg.norm(pred[..., :3], dim=-1) / torch.clamp(torch.linalg.norm(l9[..., :3], dim=-1), 1e-2, 1e2)
         lt = l9[..., :3] * torch.clamp(ratio.unsqueeze(1), 1e-2, 1e2)
         lout = torch.cat([lt, l9[..., 3:], nc], dim=-1)
-        hid = ops.linear_cat_tail(feats, torch.cat([pred, lout], dim=-1), mp[0].weight, mp[0].bias, ACT_RELU)
+        hid = ops.linear_cat_tail(feats, torch.cat([pred, lout], dim=-1), mp[0], ACT_RELU)
         wt = ops.linear(ops.linear(hid, mp[2].weight, mp[2].bias, ACT_RELU), mp[4].weight, mp[4].bias, ACT_SIGMOID)
         t_out = wt[..., :1] * pred[..., :3] + (1 - wt[..., :1]) * lout[..., :3]
         R_out = wt[..., 1:] * pred[..., 3:] + (1 - wt[..., 1:]) * lout[..., 3:-self.num_corr_size]

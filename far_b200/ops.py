@@ -76,26 +76,24 @@ def linear(x, weight, bias=None, act=L.ACT_NONE, act_cols=-1, x2=None, engine=L.
     return y.reshape(*lead, N)
 
 
-_PAD_CACHE = {}
-
-
-def linear_cat_tail(x, tail, weight, bias, act):
-    """act([x | tail] @ weight.T + bias) for a wide feature block `x` [B,K1] and a short, unaligned tail [B,K2] (the FAR
-    gates: weight [512, 35840 + 22]).  The weight row pitch K1+K2 is not a multiple of 4 floats, which would force the
-    scalar load path over 73 MB of weights; a zero-padded copy (pitch rounded up to 4) is cached per weight version."""
+def linear_cat_tail(x, tail, lin, act):
+    """act([x | tail] @ lin.weight.T + lin.bias) for a wide feature block `x` [B,K1] and a short, unaligned tail [B,K2]
+    (the FAR gates: weight [512, 35840 + 22]).  The weight row pitch K1+K2 is not a multiple of 4 floats, which would
+    force the scalar load path over 73 MB of weights; a zero-padded copy (pitch rounded up to 4) is cached ON the
+    nn.Linear module, keyed by the weight's version counter and storage pointer."""
+    weight, bias = lin.weight, lin.bias
     K1, K2 = x.shape[-1], tail.shape[-1]
     Kp = (K1 + K2 + 3) // 4 * 4
-    key = (weight.data_ptr(), weight._version, Kp)
-    wp = _PAD_CACHE.get(key)
-    if wp is None:
-        if len(_PAD_CACHE) >= 8:
-            _PAD_CACHE.clear()
+    key = (weight.data_ptr(), weight._version, Kp, str(weight.device))
+    cached = getattr(lin, "_far_padded", None)
+    if cached is None or cached[0] != key:
         wp = torch.zeros((weight.shape[0], Kp), dtype=torch.float32, device=weight.device)
         wp[:, :K1 + K2] = weight.detach()
-        _PAD_CACHE[key] = wp
+        cached = (key, wp)
+        lin._far_padded = cached
     tp = torch.zeros((tail.shape[0], Kp - K1), dtype=torch.float32, device=tail.device)
     tp[:, :K2] = tail
-    return linear(x, wp, bias, act, x2=tp)
+    return linear(x, cached[1], bias, act, x2=tp)
 
 
 def layernorm(x, gamma, beta, eps, residual=None, pre_add=None):

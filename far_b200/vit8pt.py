@@ -283,7 +283,7 @@ class ViTEss(nn.Module):
         l10 = torch.cat([l9, loftr_num_corr.detach().float().to(dev).unsqueeze(1) / 500], dim=-1)
         mp = self.moe_predictor
         tail = torch.cat([pred, l10], dim=-1)
-        hid = ops.linear_cat_tail(feats, tail, mp[0].weight, mp[0].bias, ACT_RELU)
+        hid = ops.linear_cat_tail(feats, tail, mp[0], ACT_RELU)
         wt = ops.linear(ops.linear(hid, mp[2].weight, mp[2].bias, ACT_RELU), mp[4].weight, mp[4].bias, ACT_SIGMOID)
         pred_T = wt[..., :1] * pred[..., :3] + (1 - wt[..., :1]) * l10[..., :3]
         pred_R = wt[..., 1:] * pred[..., 3:] + (1 - wt[..., 1:]) * l10[..., 3:-1]
