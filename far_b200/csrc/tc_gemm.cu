@@ -26,9 +26,19 @@ struct GemmArgs {
   const float* bias;
   int M, N, K;
   int act, act_cols;
+  int kb1;  // kRawA: number of 32-wide k-blocks that come from x1 (= K1 / 32)
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// kRawA = false: A arrives pre-split (mapAhi / mapAlo).
+// kRawA = true : mapAhi / mapAlo are the ORIGINAL fp32 activation tensors x1 [M,K1] / x2 [M,K2] (k-blocks below
+//                K1/32 come from x1, the rest from x2); four extra "converter" warps split each landed tile in shared
+//                memory (hi in place, lo into the second slot; the swizzle is a permutation of 16-byte chunks, so an
+//                elementwise pass at identical offsets preserves the UMMA layout) and publish it to the MMA warp through
+//                a third barrier after fence.proxy.async.  No split pass over the activations in HBM, half the A bytes.
+constexpr int GEMM_THREADS_RAW = NUM_THREADS + 128;
+
+template <bool kRawA>
+__global__ void __launch_bounds__(kRawA ? GEMM_THREADS_RAW : NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, GemmArgs p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -39,7 +49,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto conv_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - raw));
 
@@ -49,7 +60,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
   const int kblocks = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(conv_bar(s), 4); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -73,9 +84,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sbase = base + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-          tma_load_2d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, m0);
-          tma_load_2d(sbase + 1 * TILE_BYTES, &mapAlo, full_bar(stage), kb * BK, m0);
+          if (kRawA) {
+            mbar_arrive_expect_tx(full_bar(stage), 3 * TILE_BYTES);
+            if (kb < p.kb1) tma_load_2d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, m0);
+            else tma_load_2d(sbase + 0 * TILE_BYTES, &mapAlo, full_bar(stage), (kb - p.kb1) * BK, m0);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, m0);
+            tma_load_2d(sbase + 1 * TILE_BYTES, &mapAlo, full_bar(stage), kb * BK, m0);
+          }
           tma_load_2d(sbase + 2 * TILE_BYTES, &mapBhi, full_bar(stage), kb * BK, n0);
           tma_load_2d(sbase + 3 * TILE_BYTES, &mapBlo, full_bar(stage), kb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -98,7 +115,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         const uint32_t tmem_main = tmem_base + (uint32_t)(acc * 2 * BN);
         const uint32_t tmem_small = tmem_main + (uint32_t)BN;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(kRawA ? conv_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sbase = base + stage * STAGE_BYTES;
           const uint64_t dAhi = make_kmajor_sw128_desc(sbase + 0 * TILE_BYTES);
@@ -117,6 +134,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         }
         umma_commit(tfull_bar(acc));      // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (kRawA && warp >= 6) {
+    // ===================== converter warps (6..9): x -> (hi, lo) in shared memory =====================
+    const int ct = threadIdx.x - 6 * 32;  // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        unsigned char* sa = smem_dyn + (base + stage * STAGE_BYTES - raw);
+        float4* a4 = reinterpret_cast<float4*>(sa);
+        float4* l4 = reinterpret_cast<float4*>(sa + TILE_BYTES);
+#pragma unroll
+        for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+          const float4 v = a4[ct + i * 128];
+          float4 h;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          a4[ct + i * 128] = h;
+          l4[ct + i * 128] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -286,23 +331,34 @@ int tc_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int 
   float* whi = reinterpret_cast<float*>(base + 2 * al((size_t)M * K * 4));
   float* wlo = reinterpret_cast<float*>(base + 2 * al((size_t)M * K * 4) + al((size_t)N * K * 4));
   const int sblocks = kNumSMs * 8;
-  split_tf32_kernel<<<sblocks, 256, 0, st>>>(x1, ldx1, K1, x2, ldx2, K2, M, xhi, xlo);
-  FAR_CHECK_LAUNCH();
+  // raw-A path: TMA reads the activations in place (contiguous rows, 16-byte pitch, whole 32-wide k-blocks per source)
+  static const bool raw_off = getenv("FAR_TC_PRESPLIT") != nullptr;
+  const bool rawA = !raw_off && ldx1 == K1 && K1 % BK == 0 && (reinterpret_cast<uintptr_t>(x1) & 15u) == 0 &&
+                    (x2 == nullptr || (ldx2 == K2 && (reinterpret_cast<uintptr_t>(x2) & 15u) == 0));
+  if (!rawA) {
+    split_tf32_kernel<<<sblocks, 256, 0, st>>>(x1, ldx1, K1, x2, ldx2, K2, M, xhi, xlo);
+    FAR_CHECK_LAUNCH();
+  }
   split_tf32_kernel<<<sblocks, 256, 0, st>>>(W, ldw, K, nullptr, 0, 0, N, whi, wlo);
   FAR_CHECK_LAUNCH();
   CUtensorMap mAhi, mAlo, mBhi, mBlo;
-  if (!make_map(&mAhi, xhi, M, K) || !make_map(&mAlo, xlo, M, K) || !make_map(&mBhi, whi, N, K) ||
-      !make_map(&mBlo, wlo, N, K))
-    return FAR_ERR_CUDA;
+  bool ok = make_map(&mBhi, whi, N, K) && make_map(&mBlo, wlo, N, K);
+  if (rawA) ok = ok && make_map(&mAhi, x1, M, K1) && make_map(&mAlo, x2 ? x2 : x1, M, x2 ? K2 : K1);
+  else ok = ok && make_map(&mAhi, xhi, M, K) && make_map(&mAlo, xlo, M, K);
+  if (!ok) return FAR_ERR_CUDA;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     attr_set = true;
   }
-  GemmArgs p{y, ldy, bias, M, N, K, act, act_cols};
+  GemmArgs p{y, ldy, bias, M, N, K, act, act_cols, K1 / BK};
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, p);
+  if (rawA)
+    tc_gemm_kernel<true><<<grid, GEMM_THREADS_RAW, SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, p);
+  else
+    tc_gemm_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, p);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }
