@@ -251,30 +251,29 @@ __global__ void __launch_bounds__(32 * H) la_apply_allheads_kernel(const float* 
     reinterpret_cast<float4*>(&Qs[r][0])[c4] = qv;
   }
   __syncthreads();
+  // lane e keeps column e of this head's KV (32 registers) and Ksum[e]; per token the Q row is read as eight broadcast
+  // float4 loads (one shared-memory wavefront each) and the denominator comes from a 5-step warp reduction:
+  // ~9 LDS + 32 FMA + 5 SHFL per token per warp (the previous version issued 9 LDS per 4 d and recomputed den in
+  // every lane: LDS-bound at ~400 us per call).
   const float* kvh = KV + h * KVP;
-  const float* ksh = Ksum + h * D;
-  for (int r0 = 0; r0 < cnt; r0 += 4) {  // 4 tokens at a time: KV[d][lane] is loaded once for all four
-    float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+  float kv[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) kv[d] = kvh[d * (D + 1) + lane];
+  const float ks = Ksum[h * D + lane];
+  for (int r = 0; r < cnt; ++r) {
+    const float* qr = &Qs[r][h * D];
+    float den = qr[lane] * ks;
+    float num = 0.f;
 #pragma unroll
     for (int d4 = 0; d4 < D; d4 += 4) {
-      float4 qq[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) qq[i] = *reinterpret_cast<const float4*>(&Qs[min(r0 + i, LA2_T - 1)][h * D + d4]);
-      const float4 ks = *reinterpret_cast<const float4*>(&ksh[d4]);
-      const float kv0 = kvh[(d4 + 0) * (D + 1) + lane], kv1 = kvh[(d4 + 1) * (D + 1) + lane],
-                  kv2 = kvh[(d4 + 2) * (D + 1) + lane], kv3 = kvh[(d4 + 3) * (D + 1) + lane];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        num[i] = fmaf(qq[i].x, kv0, num[i]); num[i] = fmaf(qq[i].y, kv1, num[i]);
-        num[i] = fmaf(qq[i].z, kv2, num[i]); num[i] = fmaf(qq[i].w, kv3, num[i]);
-        den[i] = fmaf(qq[i].x, ks.x, den[i]); den[i] = fmaf(qq[i].y, ks.y, den[i]);
-        den[i] = fmaf(qq[i].z, ks.z, den[i]); den[i] = fmaf(qq[i].w, ks.w, den[i]);
-      }
+      const float4 qq = *reinterpret_cast<const float4*>(qr + d4);
+      num = fmaf(qq.x, kv[d4 + 0], num);
+      num = fmaf(qq.y, kv[d4 + 1], num);
+      num = fmaf(qq.z, kv[d4 + 2], num);
+      num = fmaf(qq.w, kv[d4 + 3], num);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (r0 + i < cnt)
-        out[((size_t)n * L + l0 + r0 + i) * ldo + h * D + lane] = num[i] * (1.f / (den[i] + eps)) * (float)S;
+    den = warp_sum(den);
+    out[((size_t)n * L + l0 + r) * ldo + h * D + lane] = num * (1.f / (den + eps)) * (float)S;
   }
 }
 

@@ -27,6 +27,7 @@ struct GemmArgs {
   int M, N, K;
   int act, act_cols;
   int kb1;  // kRawA: number of 32-wide k-blocks that come from x1 (= K1 / 32)
+  int dbg;  // diagnostics (env FAR_TC_DBG): 1 = skip global stores, 2 = skip the whole epilogue body, 4 = skip MMAs
 };
 
 // kRawA = false: A arrives pre-split (mapAhi / mapAlo).
@@ -123,7 +124,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
           const uint64_t dBhi = make_kmajor_sw128_desc(sbase + 2 * TILE_BYTES);
           const uint64_t dBlo = make_kmajor_sw128_desc(sbase + 3 * TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
+          for (int k = 0; k < ((p.dbg & 4) ? 0 : BK / UMMA_K); ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128-byte swizzle row
             umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
             umma_tf32(tmem_small, dAhi + koff, dBlo + koff, kIdescTf32, 1u);
@@ -177,7 +178,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < ((p.dbg & 2) ? 0 : BN / 32); ++c) {
         uint32_t v[32], vs[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
         tmem_ld32(taddr, v);
@@ -187,15 +188,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         // global store instruction writes four full 128-byte row segments (row-per-thread 16-byte stores measured
         // ~20 us per tile: partial-sector writes).
         __syncwarp();
+        // Branch-free fast path (whole chunk inside N, one activation for the whole chunk): per-element control flow
+        // here cost ~20 us per tile with one epilogue warp per scheduler (measured with FAR_TC_DBG).
+        const int act_here = (col0 + 32 <= actc) ? p.act : ((col0 >= actc) ? FAR_ACT_NONE : -1);
+        if (col0 + 32 <= p.N && act_here >= 0) {
+          float t[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int col = col0 + e;
-          float t = __uint_as_float(v[e]) + __uint_as_float(vs[e]);
-          if (col < p.N) {
-            if (p.bias) t += __ldg(p.bias + col);
-            if (col < actc) t = apply_act(t, p.act);
+          for (int e = 0; e < 32; ++e) t[e] = __uint_as_float(v[e]) + __uint_as_float(vs[e]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) t[e] += __ldg(p.bias + col0 + e);
           }
-          stg[lane * 33 + e] = t;
+          switch (act_here) {
+            case FAR_ACT_RELU:
+#pragma unroll
+              for (int e = 0; e < 32; ++e) t[e] = fmaxf(t[e], 0.f);
+              break;
+            case FAR_ACT_GELU:
+#pragma unroll
+              for (int e = 0; e < 32; ++e) t[e] = 0.5f * t[e] * (1.f + erff(t[e] * 0.70710678118654752440f));
+              break;
+            case FAR_ACT_ELU1:
+#pragma unroll
+              for (int e = 0; e < 32; ++e) t[e] = t[e] > 0.f ? t[e] + 1.f : expm1f(t[e]) + 1.f;
+              break;
+            case FAR_ACT_SIGMOID:
+#pragma unroll
+              for (int e = 0; e < 32; ++e) t[e] = 1.f / (1.f + expf(-t[e]));
+              break;
+            default:
+              break;
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) stg[lane * 33 + e] = t[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int col = col0 + e;
+            float t = __uint_as_float(v[e]) + __uint_as_float(vs[e]);
+            if (col < p.N) {
+              if (p.bias) t += __ldg(p.bias + col);
+              if (col < actc) t = apply_act(t, p.act);
+            }
+            stg[lane * 33 + e] = t;
+          }
         }
         __syncwarp();
         const int c4 = lane & 7;
@@ -205,7 +241,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
           const int grow = m0 + quarter * 32 + r;
           const int col = col0 + c4 * 4;
           const float* src = stg + r * 33 + c4 * 4;
-          if (grow < p.M && col < p.N) {
+          if (grow < p.M && col < p.N && !(p.dbg & 1)) {
             float* dst = p.C + (size_t)grow * p.ldc + col;
             if (vec_ok && col + 3 < p.N) {
               *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[1], src[2], src[3]);
@@ -352,7 +388,8 @@ int tc_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int 
     cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     attr_set = true;
   }
-  GemmArgs p{y, ldy, bias, M, N, K, act, act_cols, K1 / BK};
+  static const int dbg = getenv("FAR_TC_DBG") ? atoi(getenv("FAR_TC_DBG")) : 0;
+  GemmArgs p{y, ldy, bias, M, N, K, act, act_cols, K1 / BK, dbg};
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (rawA)
