@@ -18,6 +18,8 @@ for fmt in ("channels_last", "contiguous"):
         m.load_state_dict(synth.synth_state_dict(m.state_dict(), 1234))
         m = m.cuda().eval()
         m.memory_format = torch.channels_last if fmt == "channels_last" else torch.contiguous_format
+        if fmt == "channels_last":
+            m = m.to(memory_format=torch.channels_last)
         if fold:
             m = fold_batchnorm(m)
         with torch.no_grad():
