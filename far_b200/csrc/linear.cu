@@ -55,6 +55,54 @@ __global__ void __launch_bounds__(kTileThreads, 2) linear_simt_kernel(LinearArgs
     return;
   }
   const int actc = p.act_cols < 0 ? p.N : p.act_cols;
+  // Tile-uniform fast path: whole tile inside N, one activation for the whole tile, vector stores legal.  Keeps the
+  // epilogue free of per-element control flow (which dominated the tcgen05 epilogue until it was removed there).
+  const int act_tile = (n0 + TBN <= actc) ? p.act : ((n0 >= actc) ? FAR_ACT_NONE : -1);
+  if (n0 + TBN <= p.N && act_tile >= 0 && ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15u) == 0)) {
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float b = __ldg(p.bias + n0 + tile_col(tx, j));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i][j] += b;
+      }
+    }
+    if (p.rowbias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = min(m0 + tile_row(ty, i), p.M - 1);
+        const float* rb = p.rowbias + (size_t)(r / p.rowbias_group) * p.N + n0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] += __ldg(rb + tile_col(tx, j));
+      }
+    }
+    switch (act_tile) {
+      case FAR_ACT_RELU:
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaxf(acc[i][j], 0.f);
+        break;
+      case FAR_ACT_NONE:
+        break;
+      default:
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = apply_act(acc[i][j], act_tile);
+        break;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = m0 + tile_row(ty, i);
+      if (r < p.M) {
+        float* dst = p.y + (size_t)r * p.ldy + n0;
+        *reinterpret_cast<float4*>(dst + tile_col(tx, 0)) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(dst + tile_col(tx, 4)) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = m0 + tile_row(ty, i);

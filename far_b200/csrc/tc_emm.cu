@@ -82,13 +82,17 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   const uint32_t q_base = base;
   const uint32_t st_base = base + E_Q_BYTES;
   const uint32_t bar_base = st_base + 2 * E_STAGE;
-  const uint32_t q_full = bar_base + 0, s_full = bar_base + 8, p_full = bar_base + 16, p_empty = bar_base + 24,
-                 t_full = bar_base + 32;
-  auto kv_full = [&](int s) { return bar_base + 40u + 8u * s; };
-  auto kv_empty = [&](int s) { return bar_base + 56u + 8u * s; };
-  const uint32_t tmem_slot = bar_base + 72;
+  const uint32_t q_full = bar_base + 0, t_full = bar_base + 8;
+  auto k_full = [&](int s) { return bar_base + 16u + 8u * s; };
+  auto k_empty = [&](int s) { return bar_base + 32u + 8u * s; };
+  auto v_full = [&](int s) { return bar_base + 48u + 8u * s; };
+  auto v_empty = [&](int s) { return bar_base + 64u + 8u * s; };
+  auto s_full = [&](int b) { return bar_base + 80u + 8u * b; };
+  auto p_full = [&](int b) { return bar_base + 96u + 8u * b; };
+  auto sp_empty = [&](int b) { return bar_base + 112u + 8u * b; };
+  const uint32_t tmem_slot = bar_base + 128;
   unsigned char* gen_bar = smem_dyn + (bar_base - raw);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_bar + 72);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_bar + 128);
   float* cls = reinterpret_cast<float*>(gen_bar + 256);          // [EBJ] column lse of the current j-tile
   unsigned char* gen_st = smem_dyn + (st_base - raw);            // final stage aliases the K / V' ring
   float(*Ts)[ETP] = reinterpret_cast<float(*)[ETP]>(gen_st);
@@ -101,8 +105,11 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   const int JT = (p.N + EBJ - 1) / EBJ;
 
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(p_empty, 1); mbar_init(t_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    mbar_init(q_full, 1); mbar_init(t_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(p_full(s), 8); mbar_init(sp_empty(s), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -113,8 +120,11 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tS_main = tmem_base, tS_cross = tmem_base + 64, tP_hi = tmem_base + 128, tP_lo = tmem_base + 192,
-                 tT_main = tmem_base + 256, tT_cross = tmem_base + 352;
+  // TMEM columns: S/P buffer b: main [128b, 128b+64) cross [128b+64, 128b+128) -- the softmax warps overwrite S with
+  // P (hi over main, lo over cross) in place, so two buffers let S(jt+1) run on the tensor pipe while the softmax of
+  // tile jt and then T += P V'(jt) proceed; T_main [256,352), T_cross [352,448).
+  auto tSP = [&](int b) { return tmem_base + (uint32_t)(b * 128); };
+  const uint32_t tT_main = tmem_base + 256, tT_cross = tmem_base + 352;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -124,17 +134,27 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         tma_load_4d(q_base + (kb * 2 + 0) * TILE_BYTES, &mapQhi, q_full, kb * BK, i0, g0, g1);
         tma_load_4d(q_base + (kb * 2 + 1) * TILE_BYTES, &mapQlo, q_full, kb * BK, i0, g0, g1);
       }
-      for (int jt = 0; jt < JT; ++jt) {
+      for (int jt = 0; jt < JT; ++jt) {  // lane 0: K tiles (freed as soon as S(jt) retires)
         const int st = jt & 1;
         const uint32_t ph = (uint32_t)((jt >> 1) & 1);
-        mbar_wait(kv_empty(st), ph ^ 1u);
-        const uint32_t kbase = st_base + st * E_STAGE, vbase = kbase + E_K_STAGE;
-        mbar_arrive_expect_tx(kv_full(st), E_STAGE);
+        mbar_wait(k_empty(st), ph ^ 1u);
+        const uint32_t kbase = st_base + st * E_STAGE;
+        mbar_arrive_expect_tx(k_full(st), E_K_STAGE);
         for (int kb = 0; kb < 2; ++kb) {
-          tma_load_4d(kbase + (kb * 2 + 0) * E_KT, &mapKhi, kv_full(st), kb * BK, jt * EBJ, g0, g1);
-          tma_load_4d(kbase + (kb * 2 + 1) * E_KT, &mapKlo, kv_full(st), kb * BK, jt * EBJ, g0, g1);
-          tma_load_3d(vbase + (kb * 2 + 0) * E_VT, &mapVhi, kv_full(st), jt * EBJ + kb * BK, 0, g);
-          tma_load_3d(vbase + (kb * 2 + 1) * E_VT, &mapVlo, kv_full(st), jt * EBJ + kb * BK, 0, g);
+          tma_load_4d(kbase + (kb * 2 + 0) * E_KT, &mapKhi, k_full(st), kb * BK, jt * EBJ, g0, g1);
+          tma_load_4d(kbase + (kb * 2 + 1) * E_KT, &mapKlo, k_full(st), kb * BK, jt * EBJ, g0, g1);
+        }
+      }
+    } else if (lane == 1) {
+      for (int jt = 0; jt < JT; ++jt) {  // lane 1: V'^T tiles (freed when T += P V'(jt) retires)
+        const int st = jt & 1;
+        const uint32_t ph = (uint32_t)((jt >> 1) & 1);
+        mbar_wait(v_empty(st), ph ^ 1u);
+        const uint32_t vbase = st_base + st * E_STAGE + E_K_STAGE;
+        mbar_arrive_expect_tx(v_full(st), E_V_STAGE);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_3d(vbase + (kb * 2 + 0) * E_VT, &mapVhi, v_full(st), jt * EBJ + kb * BK, 0, g);
+          tma_load_3d(vbase + (kb * 2 + 1) * E_VT, &mapVlo, v_full(st), jt * EBJ + kb * BK, 0, g);
         }
       }
     }
@@ -144,13 +164,13 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       constexpr uint32_t idS = idesc_tf32(BM, EBJ), idT = idesc_tf32(BM, EDVP);
       mbar_wait(q_full, 0);
       tc_fence_after();
-      for (int jt = 0; jt < JT; ++jt) {
+      auto issue_S = [&](int jt) {   // S(jt) = Q K(jt)^T into S/P buffer jt & 1
         const int st = jt & 1;
-        const uint32_t ph = (uint32_t)((jt >> 1) & 1);
-        mbar_wait(kv_full(st), ph);
+        mbar_wait(k_full(st), (uint32_t)((jt >> 1) & 1));
+        if (jt >= 2) mbar_wait(sp_empty(st), (uint32_t)(((jt - 2) >> 1) & 1));  // T += P V'(jt-2) has consumed the buffer
         tc_fence_after();
-        const uint32_t kbase = st_base + st * E_STAGE, vbase = kbase + E_K_STAGE;
-        // ---- S = Q K^T (the previous iteration's p_full wait guarantees the softmax warps are done with S)
+        const uint32_t kbase = st_base + st * E_STAGE;
+        const uint32_t tS_main = tSP(st), tS_cross = tSP(st) + 64;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const uint64_t dQhi = make_kmajor_sw128_desc(q_base + (kb * 2 + 0) * TILE_BYTES);
@@ -165,10 +185,20 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
             umma_tf32(tS_main, dQhi + koff, dKhi + koff, idS, (kb | k) ? 1u : 0u);
           }
         }
-        umma_commit(s_full);
+        umma_commit(s_full(st));
+        umma_commit(k_empty(st));
+      };
+      issue_S(0);
+      for (int jt = 0; jt < JT; ++jt) {
+        const int st = jt & 1;
+        const uint32_t ph = (uint32_t)((jt >> 1) & 1);
+        if (jt + 1 < JT) issue_S(jt + 1);   // keeps the tensor pipe busy while the softmax warps work on tile jt
         // ---- T += P V'   (A = P from TMEM, B = V'^T tile, K = 64 keys)
-        mbar_wait(p_full, (uint32_t)(jt & 1));
+        mbar_wait(v_full(st), ph);
+        mbar_wait(p_full(st), ph);
         tc_fence_after();
+        const uint32_t vbase = st_base + st * E_STAGE + E_K_STAGE;
+        const uint32_t tP_hi = tSP(st), tP_lo = tSP(st) + 64;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const uint64_t dVhi = make_kmajor_sw128_desc(vbase + (kb * 2 + 0) * E_VT);
@@ -183,8 +213,8 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
             umma_tf32_ts(tT_main, tP_hi + acol, dVhi + koff, idT, first);
           }
         }
-        umma_commit(kv_empty(st));  // K / V' stage reusable
-        umma_commit(p_empty);       // P may be overwritten
+        umma_commit(v_empty(st));   // V' stage reusable
+        umma_commit(sp_empty(st));  // S/P buffer reusable
       }
       umma_commit(t_full);
     }
@@ -204,32 +234,30 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       const int j0 = jt * EBJ;
       if (et < EBJ) cls[et] = (j0 + et < p.N) ? p.collse[(size_t)g * p.N + j0 + et] * kL2e : 0.f;
       epi_bar2();
-      mbar_wait(s_full, (uint32_t)(jt & 1));
+      const int b = jt & 1;
+      mbar_wait(s_full(b), (uint32_t)((jt >> 1) & 1));
       tc_fence_after();
-      if (jt > 0) {  // the previous T += P V' has consumed P (it retired before S(jt), so this never stalls)
-        mbar_wait(p_empty, (uint32_t)((jt - 1) & 1));
-        tc_fence_after();
-      }
       {
-        uint32_t a[32], b[32];
-        tmem_ld32(tS_main + lane_off + (uint32_t)(half * 32), a);
-        tmem_ld32(tS_cross + lane_off + (uint32_t)(half * 32), b);
+        uint32_t a[32], bb[32];
+        const uint32_t tS = tSP(b) + lane_off + (uint32_t)(half * 32);
+        tmem_ld32(tS, a);
+        tmem_ld32(tS + 64, bb);
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          const float x = __uint_as_float(a[e]) + __uint_as_float(b[e]);
+          const float x = __uint_as_float(a[e]) + __uint_as_float(bb[e]);
           const bool ok = rvalid && (j0 + half * 32 + e) < p.N;
           const float pv = ok ? ex2a(fmaf(x, scale2x2, -(rl2 + cls[half * 32 + e]))) : 0.f;
           const uint32_t h = __float_as_uint(pv) & 0xFFFFE000u;
-          a[e] = h;                                            // hi
-          b[e] = __float_as_uint(pv - __uint_as_float(h));     // lo (exact)
+          a[e] = h;                                             // hi
+          bb[e] = __float_as_uint(pv - __uint_as_float(h));     // lo (exact)
         }
-        tmem_st32(tP_hi + lane_off + (uint32_t)(half * 32), a);
-        tmem_st32(tP_lo + lane_off + (uint32_t)(half * 32), b);
+        tmem_st32(tS, a);        // P_hi over S_main, P_lo over S_cross: same lanes / columns this thread just read
+        tmem_st32(tS + 64, bb);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(p_full(b));
       epi_bar2();  // cls is rewritten at the top of the next iteration
     }
     // ---- final stage: F_it = V'_i^T T
