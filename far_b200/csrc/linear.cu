@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) linear_simt_kernel(LinearArgs
   }
   simt_tile_mma<kVec4>(p.x1 + (size_t)m0 * p.ldx1 + kbeg, p.ldx1, mValid, p.W + (size_t)n0 * p.ldw + kbeg, p.ldw,
                        nValid, klen, sm, acc);
-  if (p.x2 != nullptr && p.K2 > 0)
+  if (p.x2 != nullptr && p.K2 > 0 && (p.splits <= 1 || z == p.splits - 1))  // K-concat tail rides with the last split
     simt_tile_mma<kVec4>(p.x2 + (size_t)m0 * p.ldx2, p.ldx2, mValid, p.W + (size_t)n0 * p.ldw + p.K1, p.ldw,
                          nValid, p.K2, sm, acc);
 
@@ -368,7 +368,7 @@ int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int l
 
   LinearArgs p{x1, ldx1, K1, x2, ldx2, K2, W, ldw, bias, y, ldy, M, N, act, act_cols, nullptr, 1, K1, rowbias,
                rowbias_group > 0 ? rowbias_group : 1};
-  if (x2 == nullptr && rowbias == nullptr) choose_splits(M, N, K1, &p.splits, &p.kchunk);
+  if (rowbias == nullptr) choose_splits(M, N, K1, &p.splits, &p.kchunk);
   if (p.splits > 1) {
     const size_t need = (size_t)p.splits * M * N * sizeof(float);
     if (workspace == nullptr || workspace_bytes < need) {  // fall back to no split rather than fail

@@ -128,6 +128,34 @@ def pos_encode_flatten(feat, pe_hwc):
     return out
 
 
+def upsample2x_add(low, skip=None):
+    """skip + F.interpolate(low, scale_factor=2., mode='bilinear', align_corners=True) on channels_last maps
+    (resnet_fpn.py:106-112).  Returns a channels_last [N,C,2H,2W] tensor."""
+    lib = L.load()
+    n, c, h, w = low.shape
+    low_ = f32c(low.permute(0, 2, 3, 1))          # no copy when low is channels_last
+    skip_ = f32c(skip.permute(0, 2, 3, 1)) if skip is not None else None
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.float32, device=low.device)
+    with _timed("far_upsample2x_add_nhwc"):
+        check(lib.far_upsample2x_add_nhwc(ptr(low_), ptr(skip_), ptr(out), n, h, w, c, stream()),
+              "far_upsample2x_add_nhwc")
+    return out.permute(0, 3, 1, 2)
+
+
+def scale_shift_act_(x, scale, shift, negative_slope):
+    """In place leaky_relu(x*scale[c] + shift[c]) on a channels_last [N,C,H,W] map (eval BatchNorm2d + LeakyReLU,
+    resnet_fpn.py:84-95)."""
+    lib = L.load()
+    n, c, h, w = x.shape
+    x_ = x.permute(0, 2, 3, 1)
+    if not x_.is_contiguous():
+        raise L.FarError("scale_shift_act_ needs a dense channels_last tensor")
+    with _timed("far_scale_shift_act_nhwc"):
+        check(lib.far_scale_shift_act_nhwc(ptr(x_), ptr(f32c(scale)) if scale is not None else None, ptr(f32c(shift)),
+                                           n * h * w, c, float(negative_slope), stream()), "far_scale_shift_act_nhwc")
+    return x
+
+
 def linear_attention(q, k, v, eps=1e-6, feature_map_applied=False):
     """LinearAttention.forward (linear_attention.py:20-52).  q [N,L,H,D]; k,v [N,S,H,D] -> [N,L,H,D]."""
     lib = L.load()

@@ -69,6 +69,18 @@ int far_layernorm_pre(const float* x, const float* pre_add, int pre_rows, const 
 int far_pos_encode_flatten(const float* feat, long long sn, long long sc, long long sh, long long sw,
                            const float* pe_hwc, float* out, int N, int C, int H, int W, void* stream);
 
+/* ---- ResNet-FPN top-down glue on channels_last (NHWC) maps ----------------------------------------------
+ * out = skip + F.interpolate(low, scale_factor=2., mode='bilinear', align_corners=True)
+ * (mp3d_loftr/src/loftr/backbone/resnet_fpn.py:106-112; skip may be NULL = plain upsample).
+ * low:[N,Hin,Win,C], skip/out:[N,2Hin,2Win,C], all dense NHWC, C % 4 == 0, 16-byte aligned. */
+int far_upsample2x_add_nhwc(const float* low, const float* skip, float* out, int N, int Hin, int Win, int C,
+                            void* stream);
+/* In place x[p,c] = leaky_relu(x[p,c]*scale[c] + shift[c], negative_slope): eval-mode BatchNorm2d (scale =
+ * gamma/sqrt(var+eps), shift = beta - mean*scale) followed by nn.LeakyReLU / nn.ReLU (slope 0)
+ * (resnet_fpn.py:84-95 layer{1,2}_outconv2).  scale may be NULL (bias only).  x:[pixels, C] NHWC, C % 4 == 0. */
+int far_scale_shift_act_nhwc(float* x, const float* scale, const float* shift, long long pixels, int C,
+                             float negative_slope, void* stream);
+
 /* ---- LinearAttention.forward (mp3d_loftr/src/loftr/loftr_module/linear_attention.py:20-52) -----------
  * q:[N,L,H*D], k,v:[N,S,H*D] (row strides ldq/ldk/ldv), out:[N,L,H*D] (ld ldo).
  * feature_map_applied != 0 means q,k already hold elu(x)+1 (fused into the projection epilogue). */

@@ -419,3 +419,44 @@ def test_mapfree_regression_mlp_vs_reference_golden(golden_dir):
     assert_close(t, to, 2e-5, 1e-4, "t vs oracle")
     assert_close(R, torch.from_numpy(gold["R"]), 2e-5, 1e-4, "R6d vs reference golden")
     assert_close(t, torch.from_numpy(gold["t"]), 2e-5, 1e-4, "t vs reference golden")
+
+
+# ------------------------------------------------------------------------------------- FPN glue (backbone)
+@pytest.mark.parametrize("n,c,h,w", [(2, 8, 3, 5), (3, 196, 15, 20), (1, 256, 60, 80)])
+def test_upsample2x_add_nhwc(n, c, h, w):
+    """resnet_fpn.py:106-112: skip + F.interpolate(low, 2x, bilinear, align_corners=True), vs torch CPU fp32."""
+    g = O.rng(n * 100 + c)
+    low, skip = O.randn(g, n, c, h, w), O.randn(g, n, c, 2 * h, 2 * w)
+    ref = skip + torch.nn.functional.interpolate(low, scale_factor=2., mode='bilinear', align_corners=True)
+    out = ops.upsample2x_add(cu(low).contiguous(memory_format=torch.channels_last),
+                             cu(skip).contiguous(memory_format=torch.channels_last))
+    assert out.shape == ref.shape
+    assert_close(out, ref, 1e-5, 1e-5, "upsample2x_add")
+    out2 = ops.upsample2x_add(cu(low).contiguous(memory_format=torch.channels_last))
+    assert_close(out2, ref - skip, 1e-5, 1e-5, "upsample2x")
+
+
+def test_scale_shift_act_nhwc():
+    g = O.rng(5)
+    x, sc, sh = O.randn(g, 2, 196, 9, 7), O.rand(g, 196) + 0.5, O.randn(g, 196)
+    ref = torch.nn.functional.leaky_relu(x * sc[None, :, None, None] + sh[None, :, None, None], 0.01)
+    xg = cu(x).contiguous(memory_format=torch.channels_last)
+    ops.scale_shift_act_(xg, cu(sc), cu(sh), 0.01)
+    assert_close(xg, ref, 1e-6, 1e-6, "scale_shift_act")
+
+
+def test_backbone_fused_eval_matches_module_graph():
+    """The eval-time fused backbone (BN folded, cuDNN conv+bias+ReLU, far_* FPN glue) against the plain module graph
+    of the same weights (resnet_fpn.py:43-119), fp32 convs (TF32 off via the fixture)."""
+    from far_b200.loftr.backbone import ResNetFPN_8_2
+    m = ResNetFPN_8_2({'initial_dim': 128, 'block_dims': [128, 196, 256]})
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), 77))
+    m = m.to(DEV).eval()
+    x = cu(O.rand(O.rng(3), 2, 1, 96, 128))
+    with torch.no_grad():
+        m.fused_eval = False
+        c0, f0 = m(x)
+        m.fused_eval = True
+        c1, f1 = m(x)
+    assert_close(c1, c0, 2e-4, 2e-4, "fused backbone coarse")
+    assert_close(f1, f0, 2e-4, 2e-4, "fused backbone fine")
