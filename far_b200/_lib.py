@@ -66,6 +66,11 @@ _SIGS = {
     "far_softmax_attention_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "far_softmax_attention": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, _P, _P, c_size_t, _P]),
     "far_pose_blend_mp3d": (c_int, [_P, _P, c_int, _P, _P, _P, c_int, _P, c_int, _P]),
+    "far_profile_num_ids": (c_int, []),
+    "far_profile_name": (ctypes.c_char_p, [c_int]),
+    "far_profile_enable": (c_int, [c_int]),
+    "far_profile_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong),
+                                 ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }
 
 _lib = None
@@ -91,6 +96,25 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def profile_enable(on):
+    check(load().far_profile_enable(int(on)), "far_profile_enable")
+
+
+def profile_read():
+    """{kernel class: dict(ms, launches, flops, bytes)} from the library's per-launch CUDA events (far_sm100.h)."""
+    lib = load()
+    out = {}
+    for i in range(lib.far_profile_num_ids()):
+        ms, fl, by = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        n = ctypes.c_ulonglong()
+        check(lib.far_profile_read(i, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl), ctypes.byref(by)),
+              "far_profile_read")
+        if n.value:
+            out[lib.far_profile_name(i).decode()] = {"ms": ms.value, "launches": n.value, "flops": fl.value,
+                                                     "bytes": by.value}
+    return out
 
 
 def check(rc, what):

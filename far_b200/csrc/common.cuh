@@ -30,6 +30,26 @@ namespace far { extern unsigned long long g_launch_count; }
 
 namespace far {
 
+// Per-kernel device timing (far_profile_* of the C ABI).  `ProfScope s(id, flops, bytes, stream);` around a launch.
+enum ProfId {
+  PROF_TC_GEMM = 0, PROF_TC_SCORE, PROF_TC_EMM_PV, PROF_LA_REDUCE, PROF_LA_APPLY, PROF_LA_SMALL, PROF_LAYERNORM,
+  PROF_LINEAR_SIMT, PROF_FINE_GATHER, PROF_FINE_MATCH, PROF_SPLIT, PROF_EMM_SIMT, PROF_SOLVER, PROF_FPN, PROF_ENC_FUSED,
+  PROF_NUM_IDS
+};
+extern bool g_prof_on;
+void prof_begin(int id, double flops, double bytes, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(int id, double flops, double bytes, cudaStream_t s) : st(s), on(g_prof_on) {
+    if (on) prof_begin(id, flops, bytes, st);
+  }
+  ~ProfScope() {
+    if (on) prof_end(st);
+  }
+};
+
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

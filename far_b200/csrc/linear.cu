@@ -401,6 +401,54 @@ using namespace far;
 
 namespace far { unsigned long long g_launch_count = 0; }
 
+// ------------------------------------------------------------------------------------------ far_profile_*
+#include <vector>
+namespace far {
+bool g_prof_on = false;
+namespace {
+struct ProfRec { int id; double flops, bytes; cudaEvent_t e0, e1; };
+std::vector<ProfRec> g_prof_recs;
+const char* kProfNames[PROF_NUM_IDS] = {
+    "tc_gemm_kernel", "tc_score_kernel", "tc_emm_pv_kernel", "la_reduce", "la_apply", "la_small_kernel", "layernorm",
+    "linear_simt_kernel", "fine_window_gather_kernel", "fine_match_kernel", "split_kernels", "emm_simt", "solver",
+    "fpn_fuse", "enc_fused_kernel"};
+void prof_clear() {
+  for (auto& r : g_prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof_recs.clear();
+}
+}  // namespace
+void prof_begin(int id, double flops, double bytes, cudaStream_t st) {
+  ProfRec r{id, flops, bytes, nullptr, nullptr};
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  g_prof_recs.push_back(r);
+}
+void prof_end(cudaStream_t st) { cudaEventRecord(g_prof_recs.back().e1, st); }
+}  // namespace far
+
+extern "C" int far_profile_num_ids(void) { return far::PROF_NUM_IDS; }
+extern "C" const char* far_profile_name(int id) { return (id >= 0 && id < far::PROF_NUM_IDS) ? far::kProfNames[id] : ""; }
+extern "C" int far_profile_enable(int on) {
+  far::prof_clear();
+  far::g_prof_on = on != 0;
+  return FAR_OK;
+}
+extern "C" int far_profile_read(int id, double* total_ms, unsigned long long* launches, double* flops, double* bytes) {
+  if (id < 0 || id >= far::PROF_NUM_IDS || !total_ms || !launches || !flops || !bytes) return FAR_ERR_ARG;
+  double ms = 0, fl = 0, by = 0;
+  unsigned long long n = 0;
+  for (auto& r : far::g_prof_recs) {
+    if (r.id != id) continue;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) return FAR_ERR_CUDA;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) return FAR_ERR_CUDA;
+    ms += t; fl += r.flops; by += r.bytes; ++n;
+  }
+  *total_ms = ms; *launches = n; *flops = fl; *bytes = by;
+  return FAR_OK;
+}
+
 extern "C" int far_abi_version(void) { return 1; }
 extern "C" unsigned long long far_launch_count(void) { return far::g_launch_count; }
 

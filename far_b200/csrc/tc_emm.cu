@@ -384,6 +384,8 @@ int tc_emm_pv(const float* qhi, const float* qlo, const float* khi, const float*
     attr = true;
   }
   EmmTcArgs p{G, H, N, d, scale, rowlse, collse, v, sb, sh, ldv, pos, Bpos, Fpart};
+  ProfScope prof(PROF_TC_EMM_PV, (double)G * (2.0 * N * N * d + 2.0 * N * N * (d + 6) + 2.0 * N * (d + 6) * (d + 6)),
+                 4.0 * G * (2.0 * N * d + (double)N * (d + 6)), st);
   tc_emm_pv_kernel<<<dim3(ceil_div(N, BM), G), E_THREADS, EMM_SMEM, st>>>(mQhi, mQlo, mKhi, mKlo, mVhi, mVlo, p);
   FAR_CHECK_LAUNCH();
   return FAR_OK;

@@ -392,6 +392,7 @@ int tc_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int 
   GemmArgs p{y, ldy, bias, M, N, K, act, act_cols, K1 / BK, dbg};
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  ProfScope prof(PROF_TC_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N), st);
   if (rawA)
     tc_gemm_kernel<true><<<grid, GEMM_THREADS_RAW, SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, p);
   else

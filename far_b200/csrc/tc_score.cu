@@ -324,6 +324,7 @@ int tc_score_lse_partials(const ScoreArgs& a, float2* rowpart, float2* colpart, 
   p.rowpart = rowpart; p.colpart = colpart;
   const int tiles = a.G * ceil_div(a.L, BM) * ceil_div(a.S, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  ProfScope prof(PROF_TC_SCORE, 2.0 * a.G * a.L * a.S * a.K, 4.0 * a.G * ((double)a.L + a.S) * a.K, st);
   tc_score_kernel<MODE_LSE><<<grid, S_THREADS, SCORE_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
@@ -342,6 +343,7 @@ int tc_match_conf(const ScoreArgs& a, const float* rowlse, const float* collse, 
   p.rowlse = rowlse; p.collse = collse; p.rowmax = rowmax; p.colmax = colmax; p.conf_out = conf_out;
   const int tiles = a.G * ceil_div(a.L, BM) * ceil_div(a.S, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  ProfScope prof(PROF_TC_SCORE, 2.0 * a.G * a.L * a.S * a.K, 4.0 * a.G * ((double)a.L + a.S) * a.K, st);
   tc_score_kernel<MODE_CONF><<<grid, S_THREADS, SCORE_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   FAR_CHECK_LAUNCH();
   return FAR_OK;

@@ -253,16 +253,31 @@ class LocalFeatureTransformerRegressor(nn.Module):
         if config['regress_loftr_layers'] > 0:
             self.loftr = LocalFeatureTransformer(config['regress'])
 
-    def forward_emm(self, feat0, feat1, loftr_preds=None, inv_loftr_preds=None):
+    def forward_trunk(self, feat0, feat1, run_loftr=True):
+        """The part of forward()/forward_emm() that is a pure function of the two feature maps (transformer.py:423-432,
+        448-456): regress LoFTR layers -> EMM CrossBlock -> outer LayerNorm -> flatten [B,35840]; with use_simple_moe
+        also `encoder` and `pose_regressor_simple_moe` (the regressed 9-D pose).  The solver prediction only enters
+        afterwards (forward_gate), so a caller that invokes the head twice on the same feature maps
+        (fine_pred_steps = 2, lightning_loftr.py:338-346) can evaluate this once per forward."""
+        if run_loftr and self.config['regress_loftr_layers'] > 0:
+            feat0, feat1 = self.loftr(feat0, feat1)
         B = feat0.shape[0]
         x = self.emm.forward_pairs(feat0, feat1)                                   # [B, 140, 256]
         features = ops.layernorm(x, self.norm.weight, self.norm.bias, self.norm.eps).reshape(B, -1)  # [B, 35840]
+        pred_reg_6d = None
+        if self.config['regress']['use_simple_moe']:
+            feats = _seq_linear(self.encoder, features, (ACT_RELU, ACT_NONE))
+            pred_reg_6d = _seq_linear(self.pose_regressor_simple_moe, feats, (ACT_RELU, ACT_NONE))
+        return features, pred_reg_6d
+
+    def forward_gate(self, trunk, loftr_preds=None, inv_loftr_preds=None):
+        """Everything that depends on the solver prediction (transformer.py:457-469): gate MLP on
+        cat([features, regressed, solver]) and the gated blend."""
+        features, pred_reg_6d = trunk
         rc = self.config['regress']
         if not rc['use_simple_moe']:
             return _seq_linear(self.pose_regressor, features, (ACT_RELU, ACT_RELU, ACT_NONE)), \
                 (features if rc['save_mlp_feats'] else None), None
-        feats = _seq_linear(self.encoder, features, (ACT_RELU, ACT_NONE))
-        pred_reg_6d = _seq_linear(self.pose_regressor_simple_moe, feats, (ACT_RELU, ACT_NONE))
         tail = torch.cat([pred_reg_6d, loftr_preds.float()], dim=-1)              # [B, 9 + pose_size_in]
         m0 = self.moe_predictor[0]
         # moe_predictor.0 on cat([features, pred, solver]): two K-segments, no [B,35862] concat (transformer.py:458-459)
@@ -280,7 +295,9 @@ class LocalFeatureTransformerRegressor(nn.Module):
                                          pose_std_6d.to(dev), rc['scale_8pt'])
         return pose_preds, (features if rc['save_mlp_feats'] else None), pred_RT_wt
 
+    def forward_emm(self, feat0, feat1, loftr_preds=None, inv_loftr_preds=None):
+        """forward_emm of the reference takes the post-`self.loftr` features (transformer.py:448)."""
+        return self.forward_gate(self.forward_trunk(feat0, feat1, run_loftr=False), loftr_preds, inv_loftr_preds)
+
     def forward(self, feat0, feat1, loftr_preds=None, inv_loftr_preds=None, mask0=None, mask1=None, F=None):
-        if self.config['regress_loftr_layers'] > 0:
-            feat0, feat1 = self.loftr(feat0, feat1)
-        return self.forward_emm(feat0, feat1, loftr_preds, inv_loftr_preds)
+        return self.forward_gate(self.forward_trunk(feat0, feat1), loftr_preds, inv_loftr_preds)

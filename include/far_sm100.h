@@ -37,6 +37,17 @@ int far_abi_version(void);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
 unsigned long long far_launch_count(void);
 
+/* ---- per-kernel device timing (measurement only; off by default) ---------------------------------------
+ * far_profile_enable(1) makes the library bracket every launch of its heavy kernels with a CUDA-event pair on the
+ * launching stream (bench.py's `roofline` entry: the dominant KERNEL's own duration, live, inside the timed region);
+ * far_profile_enable(0) stops and frees the events.  far_profile_read() synchronises the recorded events and returns,
+ * for kernel class `id` (0 <= id < far_profile_num_ids()), total device ms, launches, and the ALGORITHMIC flops and
+ * HBM bytes of those launches (the per-unit figures of SURVEY.md 8d / DESIGN.md 4).  Returns 0, or FAR_ERR_ARG. */
+int far_profile_num_ids(void);
+const char* far_profile_name(int id);
+int far_profile_enable(int on);
+int far_profile_read(int id, double* total_ms, unsigned long long* launches, double* flops, double* bytes);
+
 /* ---- nn.Linear family --------------------------------------------------------------------------------
  * y[M,N] = act( [x1 | x2] * W^T + bias ),  x1:[M,K1] (ld ldx1), x2:[M,K2] (ld ldx2, may be NULL with K2=0),
  * W:[N,K1+K2] (ld ldw), bias:[N] or NULL, act applied to columns < act_cols only (act_cols<0: all).

@@ -364,6 +364,25 @@ def test_loftr_forward_full_vs_reference_golden(golden_dir):
     assert_close(torch.from_numpy(data["priorRT"]), torch.from_numpy(gold["priorRT"]), 1e-4, 0, "priorRT")
 
 
+def test_head_trunk_reuse():
+    """Two head invocations on the same feature maps with different solver predictions (fine_pred_steps = 2): evaluating
+    the trunk once per forward must give bit-identical results to the literal re-evaluation."""
+    from far_b200.pipeline import FarPosePipeline
+    outs = []
+    for reuse in (True, False):
+        cfg = far_eval_cfg(0.0)
+        cfg["regress"]["reuse_trunk"] = reuse
+        model = LoFTR(cfg)
+        _load(model, synth.synth_state_dict(model.state_dict(), 11))
+        img0, img1 = synth.synth_pair_images(2, seed=5)
+        K = cu(synth.mp3d_intrinsics(2))
+        out = FarPosePipeline(model, K, K)(cu(img0), cu(img1))
+        outs.append(out)
+        assert ("_far_head_trunk" in out["data"]) == reuse
+    for k in ("pose", "regressed_rt", "gating", "loftr_rt"):
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
 # ------------------------------------------------------------------------------------------- 8pt-ViT / map-free heads
 def _vit_args():
     import types
