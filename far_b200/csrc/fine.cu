@@ -142,9 +142,12 @@ extern "C" int far_fine_preprocess(const float* feat_f0, const float* feat_f1, l
   float* cterm = reinterpret_cast<float*>(base + p.cterm);
 
   const long long warps = 2 * M * WW;
+  {
+  ProfScope prof(PROF_FINE_GATHER, 0.0, 4.0 * 2.0 * 2.0 * M * WW * Cf, st);
   fine_window_gather_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, st>>>(feat_f0, feat_f1, sn, sc, sh, sw, Hf, Wf,
                                                                             Cf, b_ids, i_ids, j_ids, M, W, stride, w0c,
                                                                             w1c, win);
+  }
   FAR_CHECK_LAUNCH();
   coarse_row_gather_kernel<<<(unsigned)ceil_div_ll(2 * M, 8), 256, 0, st>>>(feat_c0, feat_c1, L0, L1, Cc, b_ids, i_ids,
                                                                            j_ids, M, crow);
@@ -168,6 +171,7 @@ extern "C" int far_fine_match(const float* feat_f0, const float* feat_f1, long l
                               void* stream) {
   if (M <= 0) return FAR_OK;
   FAR_REQUIRE(feat_f0 && feat_f1 && mkpts1_c && expec_f && mkpts1_f && WW > 0 && WW <= 32 && C > 0);
+  ProfScope prof(PROF_FINE_MATCH, 2.0 * M * WW * C, 4.0 * 2.0 * M * WW * C, (cudaStream_t)stream);
   fine_match_kernel<<<(unsigned)ceil_div_ll(M, 8), 256, 0, (cudaStream_t)stream>>>(feat_f0, feat_f1, M, WW, C, mkpts1_c,
                                                                                   offset_scale, expec_f, mkpts1_f);
   FAR_CHECK_LAUNCH();

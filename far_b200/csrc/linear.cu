@@ -260,6 +260,7 @@ static void launch_layernorm(const float* x, const float* pre, int pre_rows, con
                              const float* res, float* y, int rows, int C, float eps, cudaStream_t st) {
   const int wpb = 8;
   const int grid = ceil_div(rows, wpb);
+  ProfScope prof(PROF_LAYERNORM, 8.0 * rows * C, 4.0 * rows * C * (res ? 3.0 : 2.0), st);
   if (ln_vec_ok(x, pre, g, b, res, y, C)) {
     switch (C / 128) {
       case 1: layernorm_vec_kernel<1><<<grid, wpb * 32, 0, st>>>(x, pre, pre_rows, g, b, res, y, rows, eps); return;
@@ -381,6 +382,7 @@ int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int l
   const bool vec = ptr_aligned16(x1) && ptr_aligned16(W) && (ldx1 % 4 == 0) && (ldw % 4 == 0) && (K1 % 4 == 0) &&
                    (x2 == nullptr || (ptr_aligned16(x2) && ldx2 % 4 == 0 && K2 % 4 == 0));
   dim3 grid(ceil_div(N, TBN), ceil_div(M, TBM), p.splits);
+  ProfScope prof(PROF_LINEAR_SIMT, 2.0 * M * N * (K1 + K2), 4.0 * ((double)M * (K1 + K2) + (double)N * (K1 + K2) + (double)M * N), st);
   if (vec)
     linear_simt_kernel<true><<<grid, kTileThreads, 0, st>>>(p);
   else

@@ -318,6 +318,7 @@ int linear_attention_dispatch(const float* q, int ldq, const float* k, int ldk, 
   if (L <= LA_SMALL && S <= LA_SMALL && D == 16) {
     const long long NH = (long long)N * H;
     const unsigned blocks = (unsigned)ceil_div_ll(NH, 8);
+    ProfScope prof(PROF_LA_SMALL, 4.0 * NH * ((double)L + S) * 16 * 16, 4.0 * NH * 16 * (2.0 * L + 2.0 * S), st);
     la_small_kernel<16><<<blocks, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, NH, L, S, H, applied, eps);
     FAR_CHECK_LAUNCH();
     return FAR_OK;
@@ -337,11 +338,15 @@ int linear_attention_dispatch(const float* q, int ldq, const float* k, int ldk, 
       cudaFuncSetAttribute(la_apply_allheads_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
       attr = true;
     }
-    la_reduce_allheads_kernel<HH><<<dim3(N, sp2), 32 * HH, sm1, st>>>(k, ldk, v, ldv, S, applied, chunk2, workspace);
+    {
+      ProfScope prof(PROF_LA_REDUCE, 2.0 * N * S * CC * 32, 4.0 * 2.0 * N * S * CC, st);
+      la_reduce_allheads_kernel<HH><<<dim3(N, sp2), 32 * HH, sm1, st>>>(k, ldk, v, ldv, S, applied, chunk2, workspace);
+    }
     FAR_CHECK_LAUNCH();
     const long long tot = (long long)N * HH * rec;
     la_partial_sum_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(workspace, sp2, rec, tot, summed);
     FAR_CHECK_LAUNCH();
+    ProfScope prof(PROF_LA_APPLY, 2.0 * N * L * CC * 32, 4.0 * 2.0 * N * L * CC, st);
     la_apply_allheads_kernel<HH><<<dim3(N, ceil_div(L, LA2_T)), 32 * HH, sm2, st>>>(q, ldq, out, ldo, L, S, applied, 1, eps,
                                                                                     summed);
     FAR_CHECK_LAUNCH();
