@@ -153,6 +153,7 @@ def run_far(args, rank, world, local_rank):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
     cfg, model, sd = cfg_and_weights()
+    cfg["regress"]["reuse_trunk"] = not args.no_trunk_reuse
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).eval()
     pairs = args.pairs
@@ -186,6 +187,7 @@ def run_far(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     ops.timer = ops.OpTimer()
+    _lib.profile_enable(True)  # per-kernel CUDA-event pairs inside the library (far_profile_*, include/far_sm100.h)
     launches0 = lib.far_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -198,6 +200,8 @@ def run_far(args, rank, world, local_rank):
     launches = lib.far_launch_count() - launches0
     op_times = ops.timer.summary()
     ops.timer = None
+    kern = _lib.profile_read()
+    _lib.profile_enable(False)
     nmatch = int(out["num_matches"].sum().item())
 
     # ---------------- timed region 2: end to end through the public API with host buffers ----------------
@@ -225,31 +229,53 @@ def run_far(args, rank, world, local_rank):
     total_pairs = pairs * world * args.steps
     value = total_pairs / (ms / 1e3)
     e2e = total_pairs / (ms_e2e / 1e3)
-    # dominant kernel for the roofline entry: the one with the largest share of the step
+    # dominant kernel for the roofline entry: the kernel class with the largest share of the step, timed live by the
+    # library's own CUDA events around each of its launches on the launching stream (not the C-ABI call around it)
     top = sorted(op_times.items(), key=lambda kv: -kv[1][1])
     share = {k: round(v[1] / ms, 4) for k, v in top}
+    kshare = {k: round(v["ms"] / ms, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}
     roof = None
-    if "far_emm_bilinear_attn" in op_times:
-        calls, tot = op_times["far_emm_bilinear_attn"]
-        per_call_ms = tot / calls
-        achieved = flops_emm_call(pairs) / (per_call_ms / 1e3) / 1e12
-        roof = {"kernel": "far_emm_bilinear_attn (score_lse + emm_pv kernels, both directions)", "bound": "tensor",
-                "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
-                "peak_source": f"bf16_tflops_sustained of {which} MEASURED_PEAKS.json (kernel timed inside a long step)",
-                "ms_per_call": per_call_ms, "calls_per_step": calls / args.steps, "traffic": None,
-                "share_of_step": share.get("far_emm_bilinear_attn")}
+    traffic_db = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic_db = json.load(open(tpath))
+    if kern:
+        name, k = max(kern.items(), key=lambda kv: kv[1]["ms"])
+        per_launch_s = k["ms"] / k["launches"] / 1e3
+        tensor_bound = name.startswith("tc_")
+        if tensor_bound:
+            achieved = k["flops"] / k["launches"] / per_launch_s / 1e12
+            peak, unit, src = tf_sus, "TFLOP/s", "bf16_tflops_sustained"
+        else:
+            achieved = k["bytes"] / k["launches"] / per_launch_s / 1e9
+            peak, unit, src = hbm, "GB/s", "hbm_gbs"
+        tr = traffic_db.get(name)
+        roof = {"kernel": name, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
+                "unit": unit, "frac": achieved / peak,
+                "peak_source": f"{src} of {which} MEASURED_PEAKS.json (kernel timed inside a long step)",
+                "us_per_launch": per_launch_s * 1e6, "launches_per_step": k["launches"] / args.steps,
+                "algorithmic_flops_per_launch": k["flops"] / k["launches"],
+                "algorithmic_bytes_per_launch": k["bytes"] / k["launches"],
+                "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                "traffic_source": tr["source"] if tr else None,
+                "share_of_step": kshare.get(name),
+                "note": "3xTF32 error-compensated fp32 GEMM: 3 tensor-core MMAs per algorithmic FMA, so frac <= 1/3 of "
+                        "the tf32 pipe (= 1/6 of the bf16 peak used as denominator)" if tensor_bound else None}
     line = {"metric": "image-pairs/sec @640x480", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "mp3d_loftr_far", "pairs_per_gpu": pairs, "global_pairs": pairs * world,
                        "image": "640x480 gray", "thr": 0.0, "coarse_layers": 3, "fine_pred_steps": 2,
+                       "head_trunk": "evaluated once per forward and reused by the 2nd head invocation (identical "
+                                     "outputs; --no-trunk-reuse re-evaluates it)" if not args.no_trunk_reuse else
+                                     "re-evaluated by each of the 2 head invocations",
                        "matches_per_pair": nmatch / pairs, "parallelism": f"pairs sharded dp{world}",
                        "l2": "working set (inputs 79 MB + weights 204 MB + activations >> 126 MB L2): inputs larger than L2",
                        "backbone": "cuDNN conv with TF32 allowed (the reference's torch default); all other math fp32"},
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * img0_h.numel() * 4 * world),
                     "d2h_bytes_per_step": int((pose_h.numel() * 4 + cnt_h.numel() * 8) * world),
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "op_share_of_step": share, "clocks": sampler.summary(), "roofline": roof}
+            "gpu_launches": int(launches), "op_share_of_step": share, "kernel_share_of_step": kshare, "clocks": sampler.summary(), "roofline": roof}
     if world == 1 and not args.no_cpu_baseline:
         cfg2, _, sd2 = cfg_and_weights()
         torch.set_num_threads(os.cpu_count() or 1)
@@ -274,6 +300,8 @@ def main():
     ap.add_argument("--impl", default="far", choices=["far", "reference"])
     ap.add_argument("--pairs", type=int, default=32, help="pairs per GPU per step (BASELINE configs[1]: 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-trunk-reuse", action="store_true",
+                    help="re-evaluate the FAR head trunk in both head invocations, literally as the reference does")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -11,11 +11,14 @@ int linear_attention_dispatch(const float* q, int ldq, const float* k, int ldk, 
                               int ldo, int N, int L, int S, int H, int D, float eps, int applied, float* workspace,
                               size_t workspace_bytes, cudaStream_t st);
 size_t linear_attention_ws_bytes(int N, int S, int H, int D);
+int la_reduce_summed(const float* k, int ldk, const float* v, int ldv, int N, int S, int applied, float* workspace,
+                     size_t workspace_bytes, const float** summed_out, cudaStream_t st);
+int la_fold_merge(const float* summed, const float* Wm, int N, int C, int S, float* bhi, float* blo, cudaStream_t st);
 
 static inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct LayerPlan {
-  size_t q, k, v, attn, msg, hid, la, lin, lin_bytes, total;
+  size_t q, k, v, attn, msg, hid, la, bn, lin, lin_bytes, total;
 };
 static LayerPlan plan_layer(long long N, int L, int S, int C, int nhead) {
   LayerPlan p;
@@ -28,6 +31,7 @@ static LayerPlan plan_layer(long long N, int L, int S, int C, int nhead) {
   p.msg = off; off += align_up(rowsL * C * 4);
   p.hid = off; off += align_up(rowsL * 2 * C * 4);
   p.la = off; off += align_up(linear_attention_ws_bytes((int)N, S, nhead, C / nhead));
+  p.bn = off; off += 2 * align_up((size_t)N * C * C * 4) + 1024;  // per-batch-element folded merge operand (hi | lo)
   // hi/lo operand split of the tcgen05 engine, sized for the layer's largest GEMM (mlp.0: [rows, 2C] x [2C, 2C])
   const size_t rows = rowsL > rowsS ? rowsL : rowsS;
   p.lin_bytes = tc_linear_workspace_bytes((int)rows, 2 * C, 2 * C);
@@ -63,6 +67,44 @@ extern "C" int far_loftr_encoder_layer(const float* x, const float* source, floa
   const size_t lwb = p.lin_bytes;
   const int ML = N * L, MS = N * S, D = C / nhead;
   int rc;
+  // ---- fused tensor-core schedule (coarse / regress layers: D = 32, 8 heads) ----------------------------------------
+  //   [K' | V] = source [Wk; Wv]^T  (one GEMM, elu+1 on the K' half)      -> KV, Ksum  (la_reduce, fixed-order merge)
+  //   Bn = S * KV Wm^T per batch element (la_fold_merge)                   Q'' = (elu(x Wq^T)+1) * Z   (GEMM epilogue)
+  //   message = Q'' Bn^T  (grouped GEMM: the attention apply step folded into `merge`)  -> norm1 -> mlp -> norm2 + x
+  // [K' | V] is one [MS, 2C] row-major block that spans the workspace's k and v slots.
+  static const bool fuse_env_off = getenv("FAR_ENC_UNFUSED") != nullptr;
+  bool fuse_off = fuse_env_off;
+  if (engine == 3) { fuse_off = true; engine = 2; }  // engine 3: tensor-core GEMMs, kernel-per-op schedule (A/B testing)
+  const bool fused = !fuse_off && D == 32 && nhead == 8 && engine != 1 && (engine == 2 || tc_engine_default_on()) &&
+                     tc_linear_supported(x, C, C, nullptr, 0, 0, w->wq, C, ML, C) && p.v == p.k + (size_t)MS * C * 4 &&
+                     (long long)ML * C >= 128LL * 128 * 32 && (long long)MS * C >= 128LL * 128 * 32;
+  if (fused) {
+    TcLinearEx a{};
+    a.x1 = source; a.ldx1 = C; a.K1 = C; a.W = w->wk; a.ldw = C; a.W2 = w->wv; a.N1 = C;
+    a.y = k; a.ldy = 2 * C; a.M = MS; a.N = 2 * C; a.act = FAR_ACT_ELU1; a.act_cols = C;
+    a.workspace = lw; a.workspace_bytes = lwb;
+    if ((rc = tc_linear_ex(a, st))) return rc;
+    const float* summed = nullptr;
+    if ((rc = la_reduce_summed(k, 2 * C, k + C, 2 * C, N, S, 1, la, workspace_bytes - p.la, &summed, st))) return rc;
+    char* bnb = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(base + p.bn) + 1023) & ~uintptr_t(1023));
+    float* bhi = reinterpret_cast<float*>(bnb);
+    float* blo = reinterpret_cast<float*>(bnb + align_up((size_t)N * C * C * 4));
+    if ((rc = la_fold_merge(summed, w->wmerge, N, C, S, bhi, blo, st))) return rc;
+    TcLinearEx b{};
+    b.x1 = x; b.ldx1 = C; b.K1 = C; b.W = w->wq; b.ldw = C; b.y = q; b.ldy = C; b.M = ML; b.N = C;
+    b.act = FAR_ACT_ELU1; b.act_cols = -1; b.G = N; b.L = L;
+    b.ksum = summed; b.ksum_rec = 32 * 32 + 32; b.ksum_off = 32 * 32; b.eps = 1e-6f;
+    b.workspace = lw; b.workspace_bytes = lwb;
+    if ((rc = tc_linear_ex(b, st))) return rc;
+    TcLinearEx c{};
+    c.x1 = q; c.ldx1 = C; c.K1 = C; c.Whi = bhi; c.Wlo = blo; c.b_grouped = 1; c.y = msg; c.ldy = C; c.M = ML; c.N = C;
+    c.act = FAR_ACT_NONE; c.act_cols = -1; c.G = N; c.L = L; c.workspace = lw; c.workspace_bytes = lwb;
+    if ((rc = tc_linear_ex(c, st))) return rc;
+    if ((rc = far_layernorm(msg, w->g1, w->b1, nullptr, attn, ML, C, 1e-5f, stream))) return rc;  // attn := LN(msg)
+    if ((rc = linear_dispatch(x, C, C, attn, C, C, w->wmlp0, 2 * C, nullptr, hid, 2 * C, ML, 2 * C, FAR_ACT_RELU, -1, engine, lw, lwb, st))) return rc;
+    if ((rc = linear_dispatch(hid, 2 * C, 2 * C, nullptr, 0, 0, w->wmlp2, 2 * C, nullptr, msg, C, ML, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
+    return far_layernorm(msg, w->g2, w->b2, x, out, ML, C, 1e-5f, stream);
+  }
   // q/k projections with the elu(x)+1 feature map fused into the epilogue; v plain (:55-57, linear_attention.py:33-34)
   if ((rc = linear_dispatch(x, C, C, nullptr, 0, 0, w->wq, C, nullptr, q, C, ML, C, FAR_ACT_ELU1, -1, engine, lw, lwb, st))) return rc;
   if ((rc = linear_dispatch(source, C, C, nullptr, 0, 0, w->wk, C, nullptr, k, C, MS, C, FAR_ACT_ELU1, -1, engine, lw, lwb, st))) return rc;

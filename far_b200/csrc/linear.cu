@@ -358,7 +358,8 @@ int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int l
   FAR_REQUIRE((x2 == nullptr) == (K2 == 0));
 
   // tcgen05 3xTF32 engine: TMA needs contiguous-K rows with 16-byte-multiple strides.
-  const bool tc_ok = tc_linear_supported(x1, ldx1, K1, x2, ldx2, K2, W, ldw, M, N);
+  const bool tc_ok = tc_linear_supported(x1, ldx1, K1, x2, ldx2, K2, W, ldw, M, N) && (ldy % 4 == 0) &&
+                     (reinterpret_cast<uintptr_t>(y) & 15u) == 0;  // TMA-store epilogue: 16-byte aligned output rows
   if (engine == 2 && (!tc_ok || rowbias)) return FAR_ERR_ARG;
   const bool tc_ws_ok = workspace != nullptr && workspace_bytes >= tc_linear_workspace_bytes(M, N, K1 + K2);
   if (!rowbias && (engine == 2 || (engine == 0 && tc_ok && tc_ws_ok && tc_linear_preferred(M, N, K1 + K2) &&

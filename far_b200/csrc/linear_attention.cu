@@ -367,6 +367,77 @@ int linear_attention_dispatch(const float* q, int ldq, const float* k, int ldk, 
   return FAR_OK;
 }
 
+// ---- pieces used by the fused encoder layer (encoder_layer.cu) ----------------------------------------------------
+// KV / Ksum reduction only (D = 32, H = 8): returns the summed records [(n*H + h)][D*D + D] (KV[d][e] with v already
+// divided by S, then Ksum[d]) inside `workspace`.
+int la_reduce_summed(const float* k, int ldk, const float* v, int ldv, int N, int S, int applied, float* workspace,
+                     size_t workspace_bytes, const float** summed_out, cudaStream_t st) {
+  constexpr int HH = 8, CC = HH * 32;
+  FAR_REQUIRE(k && v && workspace && ldk % 4 == 0 && ldv % 4 == 0 && ptr_al16(k) && ptr_al16(v));
+  if (workspace_bytes < linear_attention_ws_bytes(N, S, HH, 32) - 256) return FAR_ERR_WORKSPACE;
+  const int sp2 = la_splits_allheads(N, S);
+  const int chunk2 = ceil_div(ceil_div(S, sp2), LA2_T) * LA2_T;
+  const int rec = 32 * 32 + 32;
+  float* summed = workspace + (size_t)N * HH * sp2 * rec;
+  const size_t sm1 = (size_t)2 * LA2_T * CC * 4;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(la_reduce_allheads_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+    attr = true;
+  }
+  {
+    ProfScope prof(PROF_LA_REDUCE, 2.0 * N * S * CC * 32, 4.0 * 2.0 * N * S * CC, st);
+    la_reduce_allheads_kernel<HH><<<dim3(N, sp2), 32 * HH, sm1, st>>>(k, ldk, v, ldv, S, applied, chunk2, workspace);
+  }
+  FAR_CHECK_LAUNCH();
+  const long long tot = (long long)N * HH * rec;
+  la_partial_sum_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(workspace, sp2, rec, tot, summed);
+  FAR_CHECK_LAUNCH();
+  *summed_out = summed;
+  return FAR_OK;
+}
+
+// Folds the attention apply step into the `merge` projection (transformer.py:58, linear_attention.py:47-50):
+//   message[l, o] = sum_{h,e} (Z Q KV_h S)[l, h*32+e] Wm[o, h*32+e] = sum_{h,d} (Z Q)[l, h*32+d] * Bn[o, h*32+d],
+//   Bn[o, h*32+d] = S * sum_e KV[n,h,d,e] * Wm[o, h*32+e]      (one [C,C] matrix per batch element n)
+// written directly as the tf32 hi / lo operand pair of the tcgen05 engine.  grid (N, H), block C (thread = o).
+__global__ void __launch_bounds__(256) la_fold_merge_kernel(const float* __restrict__ summed, const float* __restrict__ Wm,
+                                                            int C, float fS, float* __restrict__ bhi,
+                                                            float* __restrict__ blo) {
+  constexpr int D = 32, REC = D * D + D;
+  __shared__ float KV[D][D + 1];
+  const int n = blockIdx.x, h = blockIdx.y, H = gridDim.y, o = threadIdx.x;
+  const float* rec = summed + (size_t)(n * H + h) * REC;
+  for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) KV[idx / D][idx % D] = rec[idx];
+  __syncthreads();
+  if (o >= C) return;
+  float w[D];
+#pragma unroll
+  for (int e = 0; e < D; e += 4) {
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(Wm + (size_t)o * C + h * D + e));
+    w[e] = w4.x; w[e + 1] = w4.y; w[e + 2] = w4.z; w[e + 3] = w4.w;
+  }
+  float* oh = bhi + ((size_t)n * C + o) * C + h * D;
+  float* ol = blo + ((size_t)n * C + o) * C + h * D;
+#pragma unroll 4
+  for (int d = 0; d < D; ++d) {
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < D; ++e) acc = fmaf(KV[d][e], w[e], acc);
+    acc *= fS;
+    const float hi = __uint_as_float(__float_as_uint(acc) & 0xFFFFE000u);
+    oh[d] = hi;
+    ol[d] = acc - hi;
+  }
+}
+
+int la_fold_merge(const float* summed, const float* Wm, int N, int C, int S, float* bhi, float* blo, cudaStream_t st) {
+  FAR_REQUIRE(summed && Wm && bhi && blo && C % 32 == 0 && C <= 256 && (reinterpret_cast<uintptr_t>(Wm) & 15u) == 0);
+  la_fold_merge_kernel<<<dim3(N, C / 32), 256, 0, st>>>(summed, Wm, C, (float)S, bhi, blo);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
 size_t linear_attention_ws_bytes(int N, int S, int H, int D) {
   const int a = la_splits(N, S, H), b = la_splits_allheads(N, S);
   return (size_t)N * H * ((a > b ? a : b) + 1) * (D * D + D) * sizeof(float) + 256;

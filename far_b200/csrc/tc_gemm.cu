@@ -5,47 +5,80 @@
 // lo = x - hi exactly) and the product is accumulated as  lo*hi + hi*lo + hi*hi  in the fp32 TMEM accumulator
 // (error ~2^-21 relative per product; SURVEY.md 7 measured an identical match set with this scheme).
 //
-// Structure (one persistent CTA per SM, 192 threads):
-//   warp 0     TMA producer : cp.async.bulk.tensor (SWIZZLE_128B, 128-row x 32-float boxes) of Ahi,Alo,Bhi,Blo into
-//                             a 3-stage shared-memory ring, mbarrier complete_tx
-//   warp 1     MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M128 x N128 x K8), 12 per
-//                             stage, accumulating into one of two 128-column TMEM accumulators; tcgen05.commit
-//                             releases the smem stage / publishes the accumulator
-//   warps 2-5  epilogue     : tcgen05.ld (32 lanes x 32 columns per warp), bias + activation, vectorised global store;
-//                             overlaps the next tile's main loop through the second accumulator
-// The hi/lo split of both operands is a separate elementwise kernel into the caller's workspace (no in-kernel
-// conversion => the main loop is pure TMA -> UMMA).
+// Structure (one persistent CTA per SM; 320 threads, 448 with the in-kernel operand split):
+//   warp 0       TMA producer : cp.async.bulk.tensor (SWIZZLE_128B, 128-row x 32-float boxes) of A (raw fp32 or
+//                               pre-split hi/lo), Bhi, Blo into a 3-stage shared-memory ring, mbarrier complete_tx
+//   warp 1       MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M128 x N128 x K8), 12 per
+//                               stage, into one of two (main | cross-term) TMEM accumulator pairs; tcgen05.commit
+//                               releases the smem stage / publishes the accumulator
+//   warps 2-9    epilogue     : two warps per TMEM lane quarter (64 columns each): tcgen05.ld 32x32b.x32 of both
+//                               accumulators, bias + activation (branch-free; optionally the linear-attention
+//                               normaliser Z), eight conflict-free STS.128 into a SWIZZLE_128B staging tile, then ONE
+//                               TMA store (cp.async.bulk.tensor ... global.shared::cta) per 32x32 block.  Overlaps the
+//                               next tile's main loop through the second accumulator pair.
+//   warps 10-13  converters   : (raw-A mode) split each landed fp32 A tile into hi (in place) and lo (second slot).
+// Grouped mode: rows are G groups of L rows (tiles never straddle a group; TMA zero-fills / clips the ragged last
+// tile of each group) and B may be a per-group [G][N][K] operand -- used to fold the linear-attention apply step into
+// the `merge` projection (encoder_layer.cu).
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
 
 namespace far {
 namespace tc {
 
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;       // 320: TMA + MMA + 8 epilogue warps
+constexpr int GEMM_THREADS_RAW = GEMM_THREADS + 128;    // + 4 converter warps
+constexpr int STG_TILE = 32 * 128;                      // one 32-row x 128-byte staging tile per epilogue warp
+constexpr size_t GEMM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_WARPS * STG_TILE + 256;
+constexpr int ACT_ELU1Z = 100;  // elu(x)+1 followed by the per-(row, head) linear-attention normaliser (D = 32)
+
 struct GemmArgs {
-  float* C; int ldc;
   const float* bias;
-  int M, N, K;
+  int M, N, K;      // M = G * L
+  int G, L;         // groups x rows per group (G = 1, L = M when ungrouped)
+  int b_grouped;    // B operand indexed by group
   int act, act_cols;
-  int kb1;  // kRawA: number of 32-wide k-blocks that come from x1 (= K1 / 32)
-  int dbg;  // diagnostics (env FAR_TC_DBG): 1 = skip global stores, 2 = skip the whole epilogue body, 4 = skip MMAs
+  int kb1;          // raw-A: number of 32-wide k-blocks that come from x1 (= K1 / 32)
+  const float* ksum; int ksum_rec, ksum_off, heads; float eps;  // ACT_ELU1Z: Ksum[(g*heads + h)*ksum_rec + ksum_off + d]
+  int dbg;          // diagnostics (env FAR_TC_DBG): 1 = skip global stores, 2 = skip the epilogue body, 4 = skip MMAs
 };
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // kRawA = false: A arrives pre-split (mapAhi / mapAlo).
 // kRawA = true : mapAhi / mapAlo are the ORIGINAL fp32 activation tensors x1 [M,K1] / x2 [M,K2] (k-blocks below
-//                K1/32 come from x1, the rest from x2); four extra "converter" warps split each landed tile in shared
-//                memory (hi in place, lo into the second slot; the swizzle is a permutation of 16-byte chunks, so an
+//                K1/32 come from x1, the rest from x2); the converter warps split each landed tile in shared memory
+//                (hi in place, lo into the second slot; the swizzle is a permutation of 16-byte chunks, so an
 //                elementwise pass at identical offsets preserves the UMMA layout) and publish it to the MMA warp through
 //                a third barrier after fence.proxy.async.  No split pass over the activations in HBM, half the A bytes.
-constexpr int GEMM_THREADS_RAW = NUM_THREADS + 128;
-
 template <bool kRawA>
-__global__ void __launch_bounds__(kRawA ? GEMM_THREADS_RAW : NUM_THREADS, 1)
+__global__ void __launch_bounds__(kRawA ? GEMM_THREADS_RAW : GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
-               const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, GemmArgs p) {
+               const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+               const __grid_constant__ CUtensorMap mapC, GemmArgs p) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  const uint32_t stg_base = base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = stg_base + EPI_WARPS * STG_TILE;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
@@ -56,13 +89,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
       reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + BM - 1) / BM;
-  const int num_tiles = tiles_m * tiles_n;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_pg = (p.L + BM - 1) / BM;  // m-tiles per group
+  const int num_tiles = p.G * tiles_pg * tiles_n;
   const int kblocks = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(conv_bar(s), 4); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it at the end
@@ -81,21 +115,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        const int tm = tile / tiles_n, n0 = (tile % tiles_n) * BN;
+        const int g = tm / tiles_pg, r0 = (tm % tiles_pg) * BM, gb = p.b_grouped ? g : 0;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sbase = base + stage * STAGE_BYTES;
           if (kRawA) {
             mbar_arrive_expect_tx(full_bar(stage), 3 * TILE_BYTES);
-            if (kb < p.kb1) tma_load_2d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, m0);
-            else tma_load_2d(sbase + 0 * TILE_BYTES, &mapAlo, full_bar(stage), (kb - p.kb1) * BK, m0);
+            if (kb < p.kb1) tma_load_4d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, r0, g, 0);
+            else tma_load_4d(sbase + 0 * TILE_BYTES, &mapAlo, full_bar(stage), (kb - p.kb1) * BK, r0, g, 0);
           } else {
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, m0);
-            tma_load_2d(sbase + 1 * TILE_BYTES, &mapAlo, full_bar(stage), kb * BK, m0);
+            tma_load_4d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, r0, g, 0);
+            tma_load_4d(sbase + 1 * TILE_BYTES, &mapAlo, full_bar(stage), kb * BK, r0, g, 0);
           }
-          tma_load_2d(sbase + 2 * TILE_BYTES, &mapBhi, full_bar(stage), kb * BK, n0);
-          tma_load_2d(sbase + 3 * TILE_BYTES, &mapBlo, full_bar(stage), kb * BK, n0);
+          tma_load_4d(sbase + 2 * TILE_BYTES, &mapBhi, full_bar(stage), kb * BK, n0, gb, 0);
+          tma_load_4d(sbase + 3 * TILE_BYTES, &mapBlo, full_bar(stage), kb * BK, n0, gb, 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -137,67 +172,82 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
-  } else if (kRawA && warp >= 6) {
-    // ===================== converter warps (6..9): x -> (hi, lo) in shared memory =====================
-    const int ct = threadIdx.x - 6 * 32;  // 0..127
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(full_bar(stage), phase);
-        unsigned char* sa = smem_dyn + (base + stage * STAGE_BYTES - raw);
-        float4* a4 = reinterpret_cast<float4*>(sa);
-        float4* l4 = reinterpret_cast<float4*>(sa + TILE_BYTES);
+  } else if (warp >= 2 + EPI_WARPS) {
+    // ===================== converter warps: x -> (hi, lo) in shared memory (raw-A mode only) =====================
+    if (kRawA) {
+      const int ct = threadIdx.x - (2 + EPI_WARPS) * 32;  // 0..127
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          unsigned char* sa = smem_dyn + (base + stage * STAGE_BYTES - raw);
+          float4* a4 = reinterpret_cast<float4*>(sa);
+          float4* l4 = reinterpret_cast<float4*>(sa + TILE_BYTES);
 #pragma unroll
-        for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
-          const float4 v = a4[ct + i * 128];
-          float4 h;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          a4[ct + i * 128] = h;
-          l4[ct + i * 128] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+            const float4 v = a4[ct + i * 128];
+            float4 h;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            a4[ct + i * 128] = h;
+            l4[ct + i * 128] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(conv_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(conv_bar(stage));
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lane window of this warp: lanes [32*quarter, 32*quarter + 32)
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;   // TMEM lane window of this warp: lanes [32*quarter, 32*quarter + 32)
+    const int chalf = ew >> 2;      // columns [64*chalf, 64*chalf + 64) of the 128-wide tile
     int acc = 0;
     uint32_t acc_phase = 0;
     const int actc = p.act_cols < 0 ? p.N : p.act_cols;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
-    float* stg = reinterpret_cast<float*>(smem_dyn + (bar_base + 256 - raw)) + (warp - 2) * (32 * 33);
+    const uint32_t stg_addr = stg_base + ew * STG_TILE;
+    unsigned char* stg = smem_dyn + (stg_addr - raw);
+    // swizzled 16-byte chunk slots of this thread's staging row (SWIZZLE_128B: chunk ^= row & 7)
+    float4* srow = reinterpret_cast<float4*>(stg + lane * 128);
+    const int sx = lane & 7;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int tm = tile / tiles_n, n0 = (tile % tiles_n) * BN;
+      const int g = tm / tiles_pg, r0 = (tm % tiles_pg) * BM;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      const bool live = !(p.dbg & 2);
 #pragma unroll 1
-      for (int c = 0; c < ((p.dbg & 2) ? 0 : BN / 32); ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = chalf * 2 + cc;
+        const int col0 = n0 + c * 32;
         uint32_t v[32], vs[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
-        tmem_ld32(taddr, v);
-        tmem_ld32(taddr + (uint32_t)BN, vs);
-        const int col0 = n0 + c * 32;
-        // bias / activation on this thread's row segment, then a 32x32 transpose through shared memory so that every
-        // global store instruction writes four full 128-byte row segments (row-per-thread 16-byte stores measured
-        // ~20 us per tile: partial-sector writes).
-        __syncwarp();
-        // Branch-free fast path (whole chunk inside N, one activation for the whole chunk): per-element control flow
-        // here cost ~20 us per tile with one epilogue warp per scheduler (measured with FAR_TC_DBG).
+        tmem_ld32_nowait(taddr, v);
+        tmem_ld32_nowait(taddr + (uint32_t)BN, vs);
+        tmem_ld_wait();
+        if (cc == 1) {  // both column blocks are in registers: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        if (!live || col0 >= p.N) continue;
+        float t[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) t[e] = __uint_as_float(v[e]) + __uint_as_float(vs[e]);
+        // one activation for the whole 32-column block, or -1: the block straddles N / act_cols (per-element path)
         const int act_here = (col0 + 32 <= actc) ? p.act : ((col0 >= actc) ? FAR_ACT_NONE : -1);
         if (col0 + 32 <= p.N && act_here >= 0) {
-          float t[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) t[e] = __uint_as_float(v[e]) + __uint_as_float(vs[e]);
           if (p.bias != nullptr) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) t[e] += __ldg(p.bias + col0 + e);
+            for (int e = 0; e < 32; e += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + e));
+              t[e] += b4.x; t[e + 1] += b4.y; t[e + 2] += b4.z; t[e + 3] += b4.w;
+            }
           }
           switch (act_here) {
             case FAR_ACT_RELU:
@@ -209,55 +259,59 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
               for (int e = 0; e < 32; ++e) t[e] = 0.5f * t[e] * (1.f + erff(t[e] * 0.70710678118654752440f));
               break;
             case FAR_ACT_ELU1:
+            case ACT_ELU1Z:
+              // elu(x) + 1 = x + 1 (x > 0) | exp(x) (x <= 0); branch-free, ex2.approx on the clamped argument
 #pragma unroll
-              for (int e = 0; e < 32; ++e) t[e] = t[e] > 0.f ? t[e] + 1.f : expm1f(t[e]) + 1.f;
+              for (int e = 0; e < 32; ++e) {
+                const float ex = exp2f(fminf(t[e], 0.f) * 1.4426950408889634f);
+                t[e] = t[e] > 0.f ? t[e] + 1.f : ex;
+              }
+              if (act_here == ACT_ELU1Z) {  // Z = 1 / (Q . Ksum + eps) for this row's head (linear_attention.py:46)
+                const float* ks = p.ksum + (size_t)(g * p.heads + (col0 >> 5)) * p.ksum_rec + p.ksum_off;
+                float den = 0.f;
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                  const float4 k4 = __ldg(reinterpret_cast<const float4*>(ks + e));
+                  den = fmaf(t[e], k4.x, den); den = fmaf(t[e + 1], k4.y, den);
+                  den = fmaf(t[e + 2], k4.z, den); den = fmaf(t[e + 3], k4.w, den);
+                }
+                const float z = 1.f / (den + p.eps);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) t[e] *= z;
+              }
               break;
             case FAR_ACT_SIGMOID:
 #pragma unroll
-              for (int e = 0; e < 32; ++e) t[e] = 1.f / (1.f + expf(-t[e]));
+              for (int e = 0; e < 32; ++e) t[e] = 1.f / (1.f + __expf(-t[e]));
               break;
             default:
               break;
           }
-#pragma unroll
-          for (int e = 0; e < 32; ++e) stg[lane * 33 + e] = t[e];
         } else {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int col = col0 + e;
-            float t = __uint_as_float(v[e]) + __uint_as_float(vs[e]);
             if (col < p.N) {
-              if (p.bias) t += __ldg(p.bias + col);
-              if (col < actc) t = apply_act(t, p.act);
+              if (p.bias) t[e] += __ldg(p.bias + col);
+              if (col < actc) t[e] = apply_act(t[e], p.act == ACT_ELU1Z ? FAR_ACT_ELU1 : p.act);
             }
-            stg[lane * 33 + e] = t;
           }
         }
+        // the previous TMA store of this warp must have finished READING the staging tile
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
-        const int c4 = lane & 7;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + (lane >> 3);
-          const int grow = m0 + quarter * 32 + r;
-          const int col = col0 + c4 * 4;
-          const float* src = stg + r * 33 + c4 * 4;
-          if (grow < p.M && col < p.N && !(p.dbg & 1)) {
-            float* dst = p.C + (size_t)grow * p.ldc + col;
-            if (vec_ok && col + 3 < p.N) {
-              *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[1], src[2], src[3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (col + e < p.N) dst[e] = src[e];
-            }
-          }
+        for (int j = 0; j < 8; ++j) srow[j ^ sx] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0 && !(p.dbg & 1) && r0 + quarter * 32 < p.L) {
+          tma_store_4d(&mapC, stg_addr, col0, r0 + quarter * 32, g, 0);  // rows >= L / cols >= N are clipped
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before exit
   }
 
   tc_fence_before();
@@ -355,50 +409,93 @@ size_t tc_linear_workspace_bytes(int M, int N, int K) {
   return 2 * tc::al((size_t)M * K * 4) + 2 * tc::al((size_t)N * K * 4) + 2048;
 }
 
-int tc_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
-              const float* bias, float* y, int ldy, int M, int N, int act, int act_cols, float* workspace,
-              size_t workspace_bytes, cudaStream_t st) {
+int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
   using namespace tc;
-  const int K = K1 + K2;
-  if (workspace == nullptr || workspace_bytes < tc_linear_workspace_bytes(M, N, K)) return FAR_ERR_WORKSPACE;
-  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
-  float* xhi = reinterpret_cast<float*>(base);
-  float* xlo = reinterpret_cast<float*>(base + al((size_t)M * K * 4));
-  float* whi = reinterpret_cast<float*>(base + 2 * al((size_t)M * K * 4));
-  float* wlo = reinterpret_cast<float*>(base + 2 * al((size_t)M * K * 4) + al((size_t)N * K * 4));
-  const int sblocks = kNumSMs * 8;
+  const int K = a.K1 + a.K2, M = a.M, N = a.N;
+  const int G = a.G > 0 ? a.G : 1, L = a.G > 0 ? a.L : M;
+  if (G * L != M) return FAR_ERR_ARG;
+  // the epilogue writes through a TMA store: 16-byte aligned rows
+  if ((a.ldy & 3) != 0 || (reinterpret_cast<uintptr_t>(a.y) & 15u) != 0) return FAR_ERR_ARG;
+  const bool presplitB = a.Whi != nullptr;
   // raw-A path: TMA reads the activations in place (contiguous rows, 16-byte pitch, whole 32-wide k-blocks per source)
   static const bool raw_off = getenv("FAR_TC_PRESPLIT") != nullptr;
-  const bool rawA = !raw_off && ldx1 == K1 && K1 % BK == 0 && (reinterpret_cast<uintptr_t>(x1) & 15u) == 0 &&
-                    (x2 == nullptr || (ldx2 == K2 && (reinterpret_cast<uintptr_t>(x2) & 15u) == 0));
+  const bool rawA = !raw_off && a.ldx1 == a.K1 && a.K1 % BK == 0 && (reinterpret_cast<uintptr_t>(a.x1) & 15u) == 0 &&
+                    (a.x2 == nullptr || (a.ldx2 == a.K2 && (reinterpret_cast<uintptr_t>(a.x2) & 15u) == 0));
+  const size_t need = (rawA ? 0 : 2 * al((size_t)M * K * 4)) + (presplitB ? 0 : 2 * al((size_t)N * K * 4)) + 2048;
+  if ((need > 2048) && (a.workspace == nullptr || a.workspace_bytes < need)) return FAR_ERR_WORKSPACE;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(a.workspace) + 1023) & ~uintptr_t(1023));
+  float* xhi = reinterpret_cast<float*>(base);
+  float* xlo = reinterpret_cast<float*>(base + al((size_t)M * K * 4));
+  char* wbase = base + (rawA ? 0 : 2 * al((size_t)M * K * 4));
+  const float* whi = a.Whi;
+  const float* wlo = a.Wlo;
+  const int sblocks = kNumSMs * 8;
   if (!rawA) {
-    split_tf32_kernel<<<sblocks, 256, 0, st>>>(x1, ldx1, K1, x2, ldx2, K2, M, xhi, xlo);
+    split_tf32_kernel<<<sblocks, 256, 0, st>>>(a.x1, a.ldx1, a.K1, a.x2, a.ldx2, a.K2, M, xhi, xlo);
     FAR_CHECK_LAUNCH();
   }
-  split_tf32_kernel<<<sblocks, 256, 0, st>>>(W, ldw, K, nullptr, 0, 0, N, whi, wlo);
-  FAR_CHECK_LAUNCH();
-  CUtensorMap mAhi, mAlo, mBhi, mBlo;
-  bool ok = make_map(&mBhi, whi, N, K) && make_map(&mBlo, wlo, N, K);
-  if (rawA) ok = ok && make_map(&mAhi, x1, M, K1) && make_map(&mAlo, x2 ? x2 : x1, M, x2 ? K2 : K1);
-  else ok = ok && make_map(&mAhi, xhi, M, K) && make_map(&mAlo, xlo, M, K);
+  if (!presplitB) {
+    float* h = reinterpret_cast<float*>(wbase);
+    float* l = reinterpret_cast<float*>(wbase + al((size_t)N * K * 4));
+    const int N1 = a.W2 ? a.N1 : N;  // rows [0,N1) from W, rows [N1,N) from W2 (fused projections, e.g. [Wk; Wv])
+    split_tf32_kernel<<<sblocks, 256, 0, st>>>(a.W, a.ldw, K, nullptr, 0, 0, N1, h, l);
+    FAR_CHECK_LAUNCH();
+    if (a.W2) {
+      split_tf32_kernel<<<sblocks, 256, 0, st>>>(a.W2, a.ldw, K, nullptr, 0, 0, N - N1, h + (size_t)N1 * K, l + (size_t)N1 * K);
+      FAR_CHECK_LAUNCH();
+    }
+    whi = h; wlo = l;
+  }
+  const int Gb = a.b_grouped ? G : 1;
+  CUtensorMap mAhi, mAlo, mBhi, mBlo, mC;
+  bool ok = make_map4(&mBhi, whi, K, N, K, Gb, (long long)N * K, 1, (long long)Gb * N * K) &&
+            make_map4(&mBlo, wlo, K, N, K, Gb, (long long)N * K, 1, (long long)Gb * N * K);
+  if (rawA) {
+    ok = ok && make_map4(&mAhi, a.x1, a.K1, L, a.K1, G, (long long)L * a.K1, 1, (long long)M * a.K1);
+    if (a.x2) ok = ok && make_map4(&mAlo, a.x2, a.K2, L, a.K2, G, (long long)L * a.K2, 1, (long long)M * a.K2);
+    else mAlo = mAhi;
+  } else {
+    ok = ok && make_map4(&mAhi, xhi, K, L, K, G, (long long)L * K, 1, (long long)M * K) &&
+         make_map4(&mAlo, xlo, K, L, K, G, (long long)L * K, 1, (long long)M * K);
+  }
+  // output: dims (N, L, G, 1), 32 x 32 boxes, SWIZZLE_128B staging
+  ok = ok && make_map4(&mC, a.y, N, L, a.ldy, G, (long long)L * a.ldy, 1, (long long)M * a.ldy, 32);
   if (!ok) return FAR_ERR_CUDA;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     attr_set = true;
   }
   static const int dbg = getenv("FAR_TC_DBG") ? atoi(getenv("FAR_TC_DBG")) : 0;
-  GemmArgs p{y, ldy, bias, M, N, K, act, act_cols, K1 / BK, dbg};
-  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  GemmArgs p{};
+  p.bias = a.bias; p.M = M; p.N = N; p.K = K; p.G = G; p.L = L; p.b_grouped = a.b_grouped ? 1 : 0;
+  p.act = a.act; p.act_cols = a.act_cols; p.kb1 = a.K1 / BK;
+  if (a.ksum != nullptr) {
+    if (a.act != FAR_ACT_ELU1 || N % 32 != 0 || (a.act_cols >= 0 && a.act_cols != N)) return FAR_ERR_ARG;
+    p.act = ACT_ELU1Z; p.ksum = a.ksum; p.ksum_rec = a.ksum_rec; p.ksum_off = a.ksum_off; p.heads = N / 32; p.eps = a.eps;
+  }
+  p.dbg = dbg;
+  const int tiles = G * ceil_div(L, BM) * ceil_div(N, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  ProfScope prof(PROF_TC_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N), st);
+  ProfScope prof(PROF_TC_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)Gb * N * K + (double)M * N), st);
   if (rawA)
-    tc_gemm_kernel<true><<<grid, GEMM_THREADS_RAW, SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, p);
+    tc_gemm_kernel<true><<<grid, GEMM_THREADS_RAW, GEMM_SMEM, st>>>(mAhi, mAlo, mBhi, mBlo, mC, p);
   else
-    tc_gemm_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, p);
+    tc_gemm_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(mAhi, mAlo, mBhi, mBlo, mC, p);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
+}
+
+int tc_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
+              const float* bias, float* y, int ldy, int M, int N, int act, int act_cols, float* workspace,
+              size_t workspace_bytes, cudaStream_t st) {
+  if (workspace == nullptr || workspace_bytes < tc_linear_workspace_bytes(M, N, K1 + K2)) return FAR_ERR_WORKSPACE;
+  TcLinearEx a{};
+  a.x1 = x1; a.ldx1 = ldx1; a.K1 = K1; a.x2 = x2; a.ldx2 = ldx2; a.K2 = K2;
+  a.W = W; a.ldw = ldw; a.bias = bias; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.act = act; a.act_cols = act_cols;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  return tc_linear_ex(a, st);
 }
 
 }  // namespace far

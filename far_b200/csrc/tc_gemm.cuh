@@ -13,4 +13,23 @@ size_t tc_linear_workspace_bytes(int M, int N, int K);
 int tc_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
               const float* bias, float* y, int ldy, int M, int N, int act, int act_cols, float* workspace,
               size_t workspace_bytes, cudaStream_t st);
+
+// Extended entry: fused weight blocks ([W; W2]), pre-split (and optionally per-group) B, grouped rows, and the
+// linear-attention normaliser fused into the elu+1 epilogue.
+struct TcLinearEx {
+  const float* x1; int ldx1, K1;
+  const float* x2; int ldx2, K2;
+  const float* W; int ldw;          // [N1 (or N), K] weights (ignored when Whi != nullptr)
+  const float* W2; int N1;          // optional second block: rows [N1, N) come from W2 [N - N1, K]
+  const float* Whi; const float* Wlo;  // pre-split B: [Gb][N][K] hi / lo (tf32-truncated / remainder)
+  int b_grouped;                    // B has one [N,K] matrix per group
+  const float* bias;
+  float* y; int ldy;
+  int M, N, act, act_cols;
+  int G, L;                         // G > 0: M = G * L rows in G groups (tiles do not straddle groups); G = 0: ungrouped
+  const float* ksum; int ksum_rec, ksum_off; float eps;  // act == ELU1 and ksum != nullptr: y = (elu(x)+1) * Z,
+                                    // Z[row, h] = 1 / (dot(y[row, 32h:32h+32], ksum[(g*N/32 + h)*ksum_rec + ksum_off : +32]) + eps)
+  float* workspace; size_t workspace_bytes;
+};
+int tc_linear_ex(const TcLinearEx& a, cudaStream_t st);
 }  // namespace far

@@ -110,13 +110,15 @@ class LoFTR(nn.Module):
         # prediction (lightning_loftr.py:338-346).  Within one forward (one `data` dict) the trunk is evaluated once and
         # reused; outputs are identical to re-evaluating it (tests/test_gpu_parity.py::test_head_trunk_reuse).
         # config['regress']['reuse_trunk'] = False restores the literal re-evaluation.
+        reuse = self.config['regress'].get('reuse_trunk', True)
         key = (feat_c0.data_ptr(), feat_c1.data_ptr(), feat_c0._version, feat_c1._version, tuple(feat_c0.shape))
-        cached = data.get('_far_head_trunk') if self.config['regress'].get('reuse_trunk', True) else None
+        cached = data.get('_far_head_trunk') if reuse else None
         if cached is not None and cached[0] == key:
             trunk = cached[1]
         else:
             trunk = self.loftr_regress.forward_trunk(feat_c0, feat_c1)
-            data['_far_head_trunk'] = (key, trunk, feat_c0, feat_c1)  # holds the maps: their storage cannot be recycled
+            if reuse:
+                data['_far_head_trunk'] = (key, trunk, feat_c0, feat_c1)  # holds the maps: storage cannot be recycled
         pred_RT, mlp_features, pred_RT_wt = self.loftr_regress.forward_gate(trunk, loftr_preds=lp, inv_loftr_preds=ilp)
         data.update({'regressed_rt': pred_RT, 'expec_rt': pred_RT[0]})
         if self.config['regress']['save_mlp_feats']:

@@ -68,7 +68,7 @@ def linear(x, weight, bias=None, act=L.ACT_NONE, act_cols=-1, x2=None, engine=L.
     w = f32c(weight)
     b = f32c(bias) if bias is not None else None
     y = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=x.device)
-    nws = lib.far_linear_workspace_bytes(M, N, K1)
+    nws = lib.far_linear_workspace_bytes(M, N, Kt)
     ws = _ws(nws, x.device)
     with _timed("far_linear"):
       check(lib.far_linear(ptr(x_), K1, K1, ptr(x2_), K2 if x2_ is not None else 0, K2, ptr(w), Kt, ptr(b), ptr(y), N,
