@@ -38,7 +38,7 @@ for name, (N, K, act, two) in {"256x256": (256, 256, ACT_NONE, False), "256x256_
                  "GBs": round(4.0 * (M * K + M * N + N * K) / us / 1e3, 0)}
 print(json.dumps(res))
 ''' % ROOT
-for dbg in ("0", "2", "4", "6"):
+for dbg in sys.argv[1:] or ("0", "2", "4", "6"):
     env = dict(os.environ, FAR_TC_DBG=dbg)
     out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
     print(f"FAR_TC_DBG={dbg}", out.stdout.strip(), out.stderr.strip()[-300:])

@@ -107,10 +107,23 @@ extern "C" int far_loftr_encoder_layer(const float* x, const float* source, floa
   }
   // q/k projections with the elu(x)+1 feature map fused into the epilogue; v plain (:55-57, linear_attention.py:33-34)
   if ((rc = linear_dispatch(x, C, C, nullptr, 0, 0, w->wq, C, nullptr, q, C, ML, C, FAR_ACT_ELU1, -1, engine, lw, lwb, st))) return rc;
-  if ((rc = linear_dispatch(source, C, C, nullptr, 0, 0, w->wk, C, nullptr, k, C, MS, C, FAR_ACT_ELU1, -1, engine, lw, lwb, st))) return rc;
-  if ((rc = linear_dispatch(source, C, C, nullptr, 0, 0, w->wv, C, nullptr, v, C, MS, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
-  if ((rc = linear_attention_dispatch(q, C, k, C, v, C, attn, C, N, L, S, nhead, D, 1e-6f, 1, la,
-                                      workspace_bytes - p.la, st))) return rc;
+  const bool kv_fused = !fuse_off && engine != 1 && (engine == 2 || tc_engine_default_on()) &&
+                        tc_linear_supported(source, C, C, nullptr, 0, 0, w->wk, C, MS, 2 * C) && C % 32 == 0 &&
+                        p.v == p.k + (size_t)MS * C * 4 && (long long)MS * 2 * C >= 128LL * 128 * 32;
+  if (kv_fused) {  // [K' | V] = source [Wk; Wv]^T in one tensor-core GEMM (source read and split once)
+    TcLinearEx a{};
+    a.x1 = source; a.ldx1 = C; a.K1 = C; a.W = w->wk; a.ldw = C; a.W2 = w->wv; a.N1 = C;
+    a.y = k; a.ldy = 2 * C; a.M = MS; a.N = 2 * C; a.act = FAR_ACT_ELU1; a.act_cols = C;
+    a.workspace = lw; a.workspace_bytes = lwb;
+    if ((rc = tc_linear_ex(a, st))) return rc;
+    if ((rc = linear_attention_dispatch(q, C, k, 2 * C, k + C, 2 * C, attn, C, N, L, S, nhead, D, 1e-6f, 1, la,
+                                        workspace_bytes - p.la, st))) return rc;
+  } else {
+    if ((rc = linear_dispatch(source, C, C, nullptr, 0, 0, w->wk, C, nullptr, k, C, MS, C, FAR_ACT_ELU1, -1, engine, lw, lwb, st))) return rc;
+    if ((rc = linear_dispatch(source, C, C, nullptr, 0, 0, w->wv, C, nullptr, v, C, MS, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
+    if ((rc = linear_attention_dispatch(q, C, k, C, v, C, attn, C, N, L, S, nhead, D, 1e-6f, 1, la,
+                                        workspace_bytes - p.la, st))) return rc;
+  }
   // merge + norm1 (:58-59)
   if ((rc = linear_dispatch(attn, C, C, nullptr, 0, 0, w->wmerge, C, nullptr, msg, C, ML, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
   if ((rc = far_layernorm(msg, w->g1, w->b1, nullptr, attn, ML, C, 1e-5f, stream))) return rc;  // attn := LN(msg)

@@ -102,13 +102,14 @@ __global__ void __launch_bounds__(256) fine_match_kernel(const float* __restrict
 }
 
 static inline size_t al(size_t v) { return (v + 255) & ~size_t(255); }
-struct FinePlan { size_t win, crow, cproj, cterm, total; };
+struct FinePlan { size_t win, crow, cproj, cterm, lin, total; };
 static FinePlan fine_plan(long long M, int WW, int Cf, int Cc) {
   FinePlan p; size_t off = 0;
   p.win = off;   off += al((size_t)2 * M * WW * Cf * 4);
   p.crow = off;  off += al((size_t)2 * M * Cc * 4);
   p.cproj = off; off += al((size_t)2 * M * Cf * 4);
   p.cterm = off; off += al((size_t)2 * M * Cf * 4);
+  p.lin = off;   off += al(2 * ((size_t)Cf * Cf * 4 + 1024) + 4096);  // tcgen05 engine: hi/lo split of merge_feat's window half
   p.total = off;
   return p;
 }
@@ -160,10 +161,13 @@ extern "C" int far_fine_preprocess(const float* feat_f0, const float* feat_f1, l
   if ((rc = linear_dispatch(cproj, Cf, Cf, nullptr, 0, 0, merge_w + Cf, 2 * Cf, merge_b, cterm, Cf, (int)(2 * M), Cf,
                             FAR_ACT_NONE, -1, 1, nullptr, 0, st))) return rc;
   const int rows = (int)(M * WW);
+  // the two big GEMMs ([M*WW, Cf] x [Cf, Cf] + per-match row bias) go to the tcgen05 engine when it applies
+  float* lin = reinterpret_cast<float*>(base + p.lin);
+  const size_t lin_bytes = p.total - p.lin;
   if ((rc = linear_dispatch_rb(win, Cf, Cf, nullptr, 0, 0, merge_w, 2 * Cf, nullptr, cterm, WW, out0, Cf, rows, Cf,
-                               FAR_ACT_NONE, -1, 1, nullptr, 0, st))) return rc;
+                               FAR_ACT_NONE, -1, 0, lin, lin_bytes, st))) return rc;
   return linear_dispatch_rb(win + (size_t)rows * Cf, Cf, Cf, nullptr, 0, 0, merge_w, 2 * Cf, nullptr,
-                            cterm + (size_t)M * Cf, WW, out1, Cf, rows, Cf, FAR_ACT_NONE, -1, 1, nullptr, 0, st);
+                            cterm + (size_t)M * Cf, WW, out1, Cf, rows, Cf, FAR_ACT_NONE, -1, 0, lin, lin_bytes, st);
 }
 
 extern "C" int far_fine_match(const float* feat_f0, const float* feat_f1, long long M, int WW, int C,

@@ -360,12 +360,14 @@ int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int l
   // tcgen05 3xTF32 engine: TMA needs contiguous-K rows with 16-byte-multiple strides.
   const bool tc_ok = tc_linear_supported(x1, ldx1, K1, x2, ldx2, K2, W, ldw, M, N) && (ldy % 4 == 0) &&
                      (reinterpret_cast<uintptr_t>(y) & 15u) == 0;  // TMA-store epilogue: 16-byte aligned output rows
-  if (engine == 2 && (!tc_ok || rowbias)) return FAR_ERR_ARG;
-  const bool tc_ws_ok = workspace != nullptr && workspace_bytes >= tc_linear_workspace_bytes(M, N, K1 + K2);
-  if (!rowbias && (engine == 2 || (engine == 0 && tc_ok && tc_ws_ok && tc_linear_preferred(M, N, K1 + K2) &&
-                                  tc_engine_default_on()))) {
-    return tc_linear(x1, ldx1, K1, x2, ldx2, K2, W, ldw, bias, y, ldy, M, N, act, act_cols, workspace,
-                     workspace_bytes, st);
+  const bool rb_ok = rowbias == nullptr || (N % 4 == 0 && (reinterpret_cast<uintptr_t>(rowbias) & 15u) == 0);
+  if (engine == 2 && (!tc_ok || !rb_ok)) return FAR_ERR_ARG;
+  const bool tc_ws_ok = workspace != nullptr &&
+                        workspace_bytes >= tc_linear_workspace_need(x1, ldx1, K1, x2, ldx2, K2, M, N);
+  if (rb_ok && (engine == 2 || (engine == 0 && tc_ok && tc_ws_ok && tc_linear_preferred(M, N, K1 + K2) &&
+                                tc_engine_default_on()))) {
+    return tc_linear(x1, ldx1, K1, x2, ldx2, K2, W, ldw, bias, rowbias, rowbias_group, y, ldy, M, N, act, act_cols,
+                     workspace, workspace_bytes, st);
   }
 
   LinearArgs p{x1, ldx1, K1, x2, ldx2, K2, W, ldw, bias, y, ldy, M, N, act, act_cols, nullptr, 1, K1, rowbias,

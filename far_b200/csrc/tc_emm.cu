@@ -47,6 +47,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nw(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -230,26 +242,43 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     const float rl2 = rvalid ? p.rowlse[(size_t)g * p.N + grow] * kL2e : 0.f;
     const float scale2x2 = 2.f * p.scale * kL2e;  // P = exp(2 s - rowlse - collse) = 2^(2 s log2e - rl2 - cl2)
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    // column lse of the j-tile, double-buffered in shared memory: tile jt+1's values are fetched from global memory
+    // while tile jt is processed (the L2 latency used to sit on the per-tile critical path), one barrier per tile.
+    if (et < EBJ) cls[et] = (et < p.N) ? p.collse[(size_t)g * p.N + et] * kL2e : 0.f;
+    epi_bar2();
     for (int jt = 0; jt < JT; ++jt) {
       const int j0 = jt * EBJ;
-      if (et < EBJ) cls[et] = (j0 + et < p.N) ? p.collse[(size_t)g * p.N + j0 + et] * kL2e : 0.f;
-      epi_bar2();
       const int b = jt & 1;
+      float cls_next = 0.f;
+      if (et < EBJ && jt + 1 < JT && j0 + EBJ + et < p.N) cls_next = p.collse[(size_t)g * p.N + j0 + EBJ + et] * kL2e;
+      const float* clsb = cls + b * EBJ;
       mbar_wait(s_full(b), (uint32_t)((jt >> 1) & 1));
       tc_fence_after();
       {
         uint32_t a[32], bb[32];
         const uint32_t tS = tSP(b) + lane_off + (uint32_t)(half * 32);
-        tmem_ld32(tS, a);
-        tmem_ld32(tS + 64, bb);
+        tmem_ld32_nw(tS, a);
+        tmem_ld32_nw(tS + 64, bb);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (rvalid && j0 + EBJ <= p.N) {   // interior tile: no per-element masking
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float x = __uint_as_float(a[e]) + __uint_as_float(bb[e]);
-          const bool ok = rvalid && (j0 + half * 32 + e) < p.N;
-          const float pv = ok ? ex2a(fmaf(x, scale2x2, -(rl2 + cls[half * 32 + e]))) : 0.f;
-          const uint32_t h = __float_as_uint(pv) & 0xFFFFE000u;
-          a[e] = h;                                             // hi
-          bb[e] = __float_as_uint(pv - __uint_as_float(h));     // lo (exact)
+          for (int e = 0; e < 32; ++e) {
+            const float x = __uint_as_float(a[e]) + __uint_as_float(bb[e]);
+            const float pv = ex2a(fmaf(x, scale2x2, -(rl2 + clsb[half * 32 + e])));
+            const uint32_t h = __float_as_uint(pv) & 0xFFFFE000u;
+            a[e] = h;                                             // hi
+            bb[e] = __float_as_uint(pv - __uint_as_float(h));     // lo (exact)
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float x = __uint_as_float(a[e]) + __uint_as_float(bb[e]);
+            const bool ok = rvalid && (j0 + half * 32 + e) < p.N;
+            const float pv = ok ? ex2a(fmaf(x, scale2x2, -(rl2 + clsb[half * 32 + e]))) : 0.f;
+            const uint32_t h = __float_as_uint(pv) & 0xFFFFE000u;
+            a[e] = h;
+            bb[e] = __float_as_uint(pv - __uint_as_float(h));
+          }
         }
         tmem_st32(tS, a);        // P_hi over S_main, P_lo over S_cross: same lanes / columns this thread just read
         tmem_st32(tS + 64, bb);
@@ -258,7 +287,8 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(b));
-      epi_bar2();  // cls is rewritten at the top of the next iteration
+      if (et < EBJ) cls[(b ^ 1) * EBJ + et] = cls_next;   // buffer b^1 was last read in iteration jt-1
+      epi_bar2();
     }
     // ---- final stage: F_it = V'_i^T T
     mbar_wait(t_full, 0);

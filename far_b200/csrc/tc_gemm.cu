@@ -41,12 +41,18 @@ struct GemmArgs {
   int act, act_cols;
   int kb1;          // raw-A: number of 32-wide k-blocks that come from x1 (= K1 / 32)
   const float* ksum; int ksum_rec, ksum_off, heads; float eps;  // ACT_ELU1Z: Ksum[(g*heads + h)*ksum_rec + ksum_off + d]
+  const float* rowbias; int rb_group;  // + rowbias[(row / rb_group) * N + col]  (fine_preprocess: per-match coarse term)
   int dbg;          // diagnostics (env FAR_TC_DBG): 1 = skip global stores, 2 = skip the epilogue body, 4 = skip MMAs
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
@@ -114,12 +120,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // L2 prefetch of the raw activation tiles PF k-blocks ahead of the shared-memory ring (cp.async.bulk.prefetch):
+      // a stage can only be refilled once its MMAs retire, so with 3 stages the HBM latency of A sat on the
+      // stage-recycling chain; with the tile already in L2 the refill is an L2 hit.
+      constexpr int PF = 6;
+      auto prefetch_a = [&](int tile_p, int kb_p) {
+        if (tile_p >= num_tiles) return;
+        const int tm_p = tile_p / tiles_n;
+        const int g_p = tm_p / tiles_pg, r0_p = (tm_p % tiles_pg) * BM;
+        if (kb_p < p.kb1) tma_prefetch_4d(&mapAhi, kb_p * BK, r0_p, g_p, 0);
+        else tma_prefetch_4d(&mapAlo, (kb_p - p.kb1) * BK, r0_p, g_p, 0);
+      };
+      if (kRawA && !(p.dbg & 64)) {
+        for (int i = 0; i < PF; ++i) prefetch_a(blockIdx.x + (i / kblocks) * gridDim.x, i % kblocks);
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile / tiles_n, n0 = (tile % tiles_n) * BN;
         const int g = tm / tiles_pg, r0 = (tm % tiles_pg) * BM, gb = p.b_grouped ? g : 0;
         for (int kb = 0; kb < kblocks; ++kb) {
+          if (kRawA && !(p.dbg & 64)) {
+            const int ahead = kb + PF;
+            prefetch_a(tile + (ahead / kblocks) * gridDim.x, ahead % kblocks);
+          }
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sbase = base + stage * STAGE_BYTES;
+          if (kRawA && (p.dbg & 24)) {  // diagnostics: 8 = skip the B loads, 16 = skip the A load
+            mbar_arrive_expect_tx(full_bar(stage), ((p.dbg & 8) ? 0 : 2 * TILE_BYTES) + ((p.dbg & 16) ? 0 : TILE_BYTES));
+            if (!(p.dbg & 16)) tma_load_4d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, r0, g, 0);
+            if (!(p.dbg & 8)) {
+              tma_load_4d(sbase + 2 * TILE_BYTES, &mapBhi, full_bar(stage), kb * BK, n0, gb, 0);
+              tma_load_4d(sbase + 3 * TILE_BYTES, &mapBlo, full_bar(stage), kb * BK, n0, gb, 0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           if (kRawA) {
             mbar_arrive_expect_tx(full_bar(stage), 3 * TILE_BYTES);
             if (kb < p.kb1) tma_load_4d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, r0, g, 0);
@@ -185,7 +219,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
           float4* a4 = reinterpret_cast<float4*>(sa);
           float4* l4 = reinterpret_cast<float4*>(sa + TILE_BYTES);
 #pragma unroll
-          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+          for (int i = 0; i < ((p.dbg & 32) ? 0 : TILE_BYTES / 16 / 128); ++i) {  // dbg 32: skip the split itself
             const float4 v = a4[ct + i * 128];
             float4 h;
             h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
@@ -241,7 +275,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         for (int e = 0; e < 32; ++e) t[e] = __uint_as_float(v[e]) + __uint_as_float(vs[e]);
         // one activation for the whole 32-column block, or -1: the block straddles N / act_cols (per-element path)
         const int act_here = (col0 + 32 <= actc) ? p.act : ((col0 >= actc) ? FAR_ACT_NONE : -1);
+        const int grow = g * p.L + r0 + quarter * 32 + lane;  // this thread's global output row
+        const bool rb_on = p.rowbias != nullptr && grow < p.M && r0 + quarter * 32 + lane < p.L;
         if (col0 + 32 <= p.N && act_here >= 0) {
+          if (rb_on) {
+            const float* rb = p.rowbias + (size_t)(grow / p.rb_group) * p.N + col0;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb + e));
+              t[e] += b4.x; t[e + 1] += b4.y; t[e + 2] += b4.z; t[e + 3] += b4.w;
+            }
+          }
           if (p.bias != nullptr) {
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
@@ -292,6 +336,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
           for (int e = 0; e < 32; ++e) {
             const int col = col0 + e;
             if (col < p.N) {
+              if (rb_on) t[e] += __ldg(p.rowbias + (size_t)(grow / p.rb_group) * p.N + col);
               if (p.bias) t[e] += __ldg(p.bias + col);
               if (col < actc) t[e] = apply_act(t[e], p.act == ACT_ELU1Z ? FAR_ACT_ELU1 : p.act);
             }
@@ -396,7 +441,7 @@ bool tc_linear_supported(const float* x1, int ldx1, int K1, const float* x2, int
   (void)x1; (void)ldx1; (void)x2; (void)ldx2; (void)W;
   const int K = K1 + K2;
   (void)M; (void)N;
-  if (K % 4 != 0 || K < 32 || ldw != K) return false;         // TMA: 16-byte row pitch; weights contiguous
+  if (K % 4 != 0 || K < 32 || ldw < K) return false;          // TMA: 16-byte row pitch (the weight split densifies W)
   return tc::get_encode() != nullptr;
 }
 
@@ -409,6 +454,19 @@ size_t tc_linear_workspace_bytes(int M, int N, int K) {
   return 2 * tc::al((size_t)M * K * 4) + 2 * tc::al((size_t)N * K * 4) + 2048;
 }
 
+static bool raw_a_ok(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2) {
+  // raw-A path: TMA reads the activations in place (contiguous rows, 16-byte pitch, whole 32-wide k-blocks per source)
+  static const bool raw_off = getenv("FAR_TC_PRESPLIT") != nullptr;
+  return !raw_off && ldx1 == K1 && K1 % tc::BK == 0 && (reinterpret_cast<uintptr_t>(x1) & 15u) == 0 &&
+         (x2 == nullptr || (ldx2 == K2 && (reinterpret_cast<uintptr_t>(x2) & 15u) == 0));
+}
+
+// exact workspace need of tc_linear for these operands (the activation split buffers are only needed off the raw-A path)
+size_t tc_linear_workspace_need(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, int M, int N) {
+  const int K = K1 + K2;
+  return (raw_a_ok(x1, ldx1, K1, x2, ldx2, K2) ? 0 : 2 * tc::al((size_t)M * K * 4)) + 2 * tc::al((size_t)N * K * 4) + 2048;
+}
+
 int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
   using namespace tc;
   const int K = a.K1 + a.K2, M = a.M, N = a.N;
@@ -417,10 +475,7 @@ int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
   // the epilogue writes through a TMA store: 16-byte aligned rows
   if ((a.ldy & 3) != 0 || (reinterpret_cast<uintptr_t>(a.y) & 15u) != 0) return FAR_ERR_ARG;
   const bool presplitB = a.Whi != nullptr;
-  // raw-A path: TMA reads the activations in place (contiguous rows, 16-byte pitch, whole 32-wide k-blocks per source)
-  static const bool raw_off = getenv("FAR_TC_PRESPLIT") != nullptr;
-  const bool rawA = !raw_off && a.ldx1 == a.K1 && a.K1 % BK == 0 && (reinterpret_cast<uintptr_t>(a.x1) & 15u) == 0 &&
-                    (a.x2 == nullptr || (a.ldx2 == a.K2 && (reinterpret_cast<uintptr_t>(a.x2) & 15u) == 0));
+  const bool rawA = raw_a_ok(a.x1, a.ldx1, a.K1, a.x2, a.ldx2, a.K2);
   const size_t need = (rawA ? 0 : 2 * al((size_t)M * K * 4)) + (presplitB ? 0 : 2 * al((size_t)N * K * 4)) + 2048;
   if ((need > 2048) && (a.workspace == nullptr || a.workspace_bytes < need)) return FAR_ERR_WORKSPACE;
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(a.workspace) + 1023) & ~uintptr_t(1023));
@@ -475,6 +530,10 @@ int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
     if (a.act != FAR_ACT_ELU1 || N % 32 != 0 || (a.act_cols >= 0 && a.act_cols != N)) return FAR_ERR_ARG;
     p.act = ACT_ELU1Z; p.ksum = a.ksum; p.ksum_rec = a.ksum_rec; p.ksum_off = a.ksum_off; p.heads = N / 32; p.eps = a.eps;
   }
+  if (a.rowbias != nullptr) {
+    if (a.rowbias_group <= 0 || N % 4 != 0 || (reinterpret_cast<uintptr_t>(a.rowbias) & 15u) != 0) return FAR_ERR_ARG;
+    p.rowbias = a.rowbias; p.rb_group = a.rowbias_group;
+  }
   p.dbg = dbg;
   const int tiles = G * ceil_div(L, BM) * ceil_div(N, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
@@ -488,12 +547,14 @@ int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
 }
 
 int tc_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
-              const float* bias, float* y, int ldy, int M, int N, int act, int act_cols, float* workspace,
-              size_t workspace_bytes, cudaStream_t st) {
-  if (workspace == nullptr || workspace_bytes < tc_linear_workspace_bytes(M, N, K1 + K2)) return FAR_ERR_WORKSPACE;
+              const float* bias, const float* rowbias, int rowbias_group, float* y, int ldy, int M, int N, int act,
+              int act_cols, float* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (workspace == nullptr || workspace_bytes < tc_linear_workspace_need(x1, ldx1, K1, x2, ldx2, K2, M, N))
+    return FAR_ERR_WORKSPACE;
   TcLinearEx a{};
   a.x1 = x1; a.ldx1 = ldx1; a.K1 = K1; a.x2 = x2; a.ldx2 = ldx2; a.K2 = K2;
   a.W = W; a.ldw = ldw; a.bias = bias; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.act = act; a.act_cols = act_cols;
+  a.rowbias = rowbias; a.rowbias_group = rowbias_group;
   a.workspace = workspace; a.workspace_bytes = workspace_bytes;
   return tc_linear_ex(a, st);
 }

@@ -10,9 +10,11 @@ bool tc_linear_preferred(int M, int N, int K);
 // whether engine=0 (auto) should pick the tensor-core engine (env FAR_TC=0 disables)
 bool tc_engine_default_on();
 size_t tc_linear_workspace_bytes(int M, int N, int K);
+// exact need for these operands (no activation split buffers when TMA can read the activations in place)
+size_t tc_linear_workspace_need(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, int M, int N);
 int tc_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
-              const float* bias, float* y, int ldy, int M, int N, int act, int act_cols, float* workspace,
-              size_t workspace_bytes, cudaStream_t st);
+              const float* bias, const float* rowbias, int rowbias_group, float* y, int ldy, int M, int N, int act,
+              int act_cols, float* workspace, size_t workspace_bytes, cudaStream_t st);
 
 // Extended entry: fused weight blocks ([W; W2]), pre-split (and optionally per-group) B, grouped rows, and the
 // linear-attention normaliser fused into the elu+1 epilogue.
@@ -29,6 +31,7 @@ struct TcLinearEx {
   int G, L;                         // G > 0: M = G * L rows in G groups (tiles do not straddle groups); G = 0: ungrouped
   const float* ksum; int ksum_rec, ksum_off; float eps;  // act == ELU1 and ksum != nullptr: y = (elu(x)+1) * Z,
                                     // Z[row, h] = 1 / (dot(y[row, 32h:32h+32], ksum[(g*N/32 + h)*ksum_rec + ksum_off : +32]) + eps)
+  const float* rowbias; int rowbias_group;  // optional: + rowbias[(row / rowbias_group) * N + col]
   float* workspace; size_t workspace_bytes;
 };
 int tc_linear_ex(const TcLinearEx& a, cudaStream_t st);

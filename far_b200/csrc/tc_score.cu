@@ -42,6 +42,19 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait2(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(S_THREADS, 1)
 tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
@@ -158,8 +171,9 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32], vs[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + half * 64 + c * 32);
-        tmem_ld32(taddr, v);
-        tmem_ld32(taddr + (uint32_t)BN, vs);
+        tmem_ld32_nowait2(taddr, v);
+        tmem_ld32_nowait2(taddr + (uint32_t)BN, vs);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int e = 0; e < 32; ++e) x[c * 32 + e] = (__uint_as_float(v[e]) + __uint_as_float(vs[e])) * p.scale2;
       }
@@ -170,10 +184,15 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       const int col0 = j0 + half * 64;
       if (MODE == MODE_LSE) {
         float m = -INFINITY;
+        if (rvalid && col0 + 64 <= p.S) {  // interior: no masking
 #pragma unroll
-        for (int e = 0; e < 64; ++e) {
-          if (!(rvalid && col0 + e < p.S)) x[e] = -INFINITY;
-          m = fmaxf(m, x[e]);
+          for (int e = 0; e < 64; ++e) m = fmaxf(m, x[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 64; ++e) {
+            if (!(rvalid && col0 + e < p.S)) x[e] = -INFINITY;
+            m = fmaxf(m, x[e]);
+          }
         }
         float sum = 0.f;
         if (m > -INFINITY) {

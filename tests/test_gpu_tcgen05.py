@@ -66,3 +66,33 @@ def test_dual_softmax_match_both_engines(engine):
         assert torch.equal(m[k].cpu(), o[k]), (k, m[k].numel(), o[k].numel())
     assert_close(m["mconf"], o["mconf"], 1e-6, 1e-4, "mconf")
     assert_close(m["conf_matrix"], o["conf_matrix"], 1e-7, 1e-4, "conf_matrix")
+
+
+@pytest.mark.parametrize("N,L,S", [(3, 1000, 1100), (2, 4800, 4800), (5, 777, 777)])
+def test_fused_encoder_layer_schedule(N, L, S):
+    """The fused tensor-core schedule of the encoder layer ([K'|V] in one GEMM, Z in the q epilogue, attention-apply
+    folded into a per-batch-element merge operand; ragged L: tiles must not straddle batch elements) against the
+    fp64 oracle and against the kernel-per-op schedule (engine 3)."""
+    from oracle import far_oracle as O
+    C, H = 256, 8
+    g = O.rng(100 + N)
+    x, src = O.randn(g, N, L, C, scale=1.5), O.randn(g, N, S, C, scale=1.5)
+    w = {}
+    for k, shp in (("q_proj", (C, C)), ("k_proj", (C, C)), ("v_proj", (C, C)), ("merge", (C, C)),
+                   ("mlp0", (2 * C, 2 * C)), ("mlp2", (C, 2 * C))):
+        w[k] = O.randn(g, *shp, scale=(2.0 / (shp[0] + shp[1])) ** 0.5)
+    for k in ("norm1_w", "norm2_w"):
+        w[k] = 1.0 + O.randn(g, C, scale=0.1)
+    for k in ("norm1_b", "norm2_b"):
+        w[k] = O.randn(g, C, scale=0.1)
+    sd = {"q_proj.weight": w["q_proj"], "k_proj.weight": w["k_proj"], "v_proj.weight": w["v_proj"],
+          "merge.weight": w["merge"], "mlp.0.weight": w["mlp0"], "mlp.2.weight": w["mlp2"],
+          "norm1.weight": w["norm1_w"], "norm1.bias": w["norm1_b"], "norm2.weight": w["norm2_w"],
+          "norm2.bias": w["norm2_b"]}
+    ref = O.loftr_encoder_layer({k: v.double() for k, v in sd.items()}, x.double(), src.double(), H)
+    wd = {k: v.cuda() for k, v in w.items()}
+    fused = ops.loftr_encoder_layer(x.cuda(), src.cuda(), wd, H, 0)
+    per_op = ops.loftr_encoder_layer(x.cuda(), src.cuda(), wd, H, 3)
+    assert_close(fused, ref, 5e-5, 1e-5, "fused schedule vs fp64 oracle")
+    assert_close(per_op, ref, 5e-5, 1e-5, "per-op schedule vs fp64 oracle")
+    assert (fused - per_op).abs().max().item() < 2e-5
