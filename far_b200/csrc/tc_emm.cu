@@ -65,8 +65,28 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-constexpr int E_THREADS = 64 + 256;         // producer warp, MMA warp, 8 softmax warps
-__device__ __forceinline__ void epi_bar2() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+constexpr int E_SM_WARPS = 16;              // softmax warps: 4 per TMEM lane quarter, 16 keys each (short S -> P latency)
+constexpr int E_SM_THREADS = 32 * E_SM_WARPS;
+constexpr int E_CW = EBJ / (E_SM_WARPS / 4);  // key columns per softmax thread (16)
+constexpr int E_THREADS = 64 + E_SM_THREADS;  // producer warp, MMA warp, softmax warps
+__device__ __forceinline__ void epi_bar2() { asm volatile("bar.sync 2, %0;" ::"n"(E_SM_THREADS) : "memory"); }
+__device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ float ex2a(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -120,7 +140,7 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     mbar_init(q_full, 1); mbar_init(t_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
-      mbar_init(s_full(s), 1); mbar_init(p_full(s), 8); mbar_init(sp_empty(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(p_full(s), E_SM_WARPS); mbar_init(sp_empty(s), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -179,7 +199,9 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       auto issue_S = [&](int jt) {   // S(jt) = Q K(jt)^T into S/P buffer jt & 1
         const int st = jt & 1;
         mbar_wait(k_full(st), (uint32_t)((jt >> 1) & 1));
-        if (jt >= 2) mbar_wait(sp_empty(st), (uint32_t)(((jt - 2) >> 1) & 1));  // T += P V'(jt-2) has consumed the buffer
+        // S(jt) overwrites the S/P buffer that T += P V'(jt-2) reads.  No wait on that MMA's completion: it was issued
+        // earlier by this same thread and tcgen05.mma instructions of one thread execute in issue order, so the
+        // write-after-read on TMEM is ordered by the pipe itself -- and the tensor pipe never drains between tiles.
         tc_fence_after();
         const uint32_t kbase = st_base + st * E_STAGE;
         const uint32_t tS_main = tSP(st), tS_cross = tSP(st) + 64;
@@ -201,10 +223,10 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         umma_commit(k_empty(st));
       };
       issue_S(0);
+      if (JT > 1) issue_S(1);
       for (int jt = 0; jt < JT; ++jt) {
         const int st = jt & 1;
         const uint32_t ph = (uint32_t)((jt >> 1) & 1);
-        if (jt + 1 < JT) issue_S(jt + 1);   // keeps the tensor pipe busy while the softmax warps work on tile jt
         // ---- T += P V'   (A = P from TMEM, B = V'^T tile, K = 64 keys)
         mbar_wait(v_full(st), ph);
         mbar_wait(p_full(st), ph);
@@ -226,14 +248,15 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
           }
         }
         umma_commit(v_empty(st));   // V' stage reusable
-        umma_commit(sp_empty(st));  // S/P buffer reusable
+        // queue S(jt+2) right behind it (same S/P buffer): the softmax warps work on tile jt+1 meanwhile
+        if (jt + 2 < JT) issue_S(jt + 2);
       }
       umma_commit(t_full);
     }
   } else {
-    // ===================== softmax / epilogue: 8 warps, thread = (query row, 32-key half of the j-tile) =========
+    // ===================== softmax / epilogue: 16 warps, thread = (query row, 16-key group of the j-tile) ========
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int cgp = (warp - 2) >> 2;           // key-column group: columns [16*cgp, 16*cgp + 16) of the j-tile
     const int row = quarter * 32 + lane;
     const int et = (warp - 2) * 32 + lane;  // 0..255
     const int grow = i0 + row;
@@ -255,33 +278,33 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       mbar_wait(s_full(b), (uint32_t)((jt >> 1) & 1));
       tc_fence_after();
       {
-        uint32_t a[32], bb[32];
-        const uint32_t tS = tSP(b) + lane_off + (uint32_t)(half * 32);
-        tmem_ld32_nw(tS, a);
-        tmem_ld32_nw(tS + 64, bb);
+        uint32_t a[E_CW], bb[E_CW];
+        const uint32_t tS = tSP(b) + lane_off + (uint32_t)(cgp * E_CW);
+        tmem_ld16_nw(tS, a);
+        tmem_ld16_nw(tS + 64, bb);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (rvalid && j0 + EBJ <= p.N) {   // interior tile: no per-element masking
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
+          for (int e = 0; e < E_CW; ++e) {
             const float x = __uint_as_float(a[e]) + __uint_as_float(bb[e]);
-            const float pv = ex2a(fmaf(x, scale2x2, -(rl2 + clsb[half * 32 + e])));
+            const float pv = ex2a(fmaf(x, scale2x2, -(rl2 + clsb[cgp * E_CW + e])));
             const uint32_t h = __float_as_uint(pv) & 0xFFFFE000u;
             a[e] = h;                                             // hi
             bb[e] = __float_as_uint(pv - __uint_as_float(h));     // lo (exact)
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
+          for (int e = 0; e < E_CW; ++e) {
             const float x = __uint_as_float(a[e]) + __uint_as_float(bb[e]);
-            const bool ok = rvalid && (j0 + half * 32 + e) < p.N;
-            const float pv = ok ? ex2a(fmaf(x, scale2x2, -(rl2 + clsb[half * 32 + e]))) : 0.f;
+            const bool ok = rvalid && (j0 + cgp * E_CW + e) < p.N;
+            const float pv = ok ? ex2a(fmaf(x, scale2x2, -(rl2 + clsb[cgp * E_CW + e]))) : 0.f;
             const uint32_t h = __float_as_uint(pv) & 0xFFFFE000u;
             a[e] = h;
             bb[e] = __float_as_uint(pv - __uint_as_float(h));
           }
         }
-        tmem_st32(tS, a);        // P_hi over S_main, P_lo over S_cross: same lanes / columns this thread just read
-        tmem_st32(tS + 64, bb);
+        tmem_st16(tS, a);        // P_hi over S_main, P_lo over S_cross: same lanes / columns this thread just read
+        tmem_st16(tS + 64, bb);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -294,7 +317,7 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     mbar_wait(t_full, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = half; c < EDVP / 32; c += 2) {
+    for (int c = cgp; c < EDVP / 32; c += E_SM_WARPS / 4) {
       uint32_t a[32], b[32];
       tmem_ld32(tT_main + lane_off + (uint32_t)(c * 32), a);
       tmem_ld32(tT_cross + lane_off + (uint32_t)(c * 32), b);
@@ -305,7 +328,7 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       const int b = g / p.H, h = g % p.H, dv = p.d + 6;
       const float* vb = p.v + (size_t)b * p.sb + (size_t)h * p.sh;
       const float* pb = p.pos + (size_t)(p.Bpos == 1 ? 0 : b) * p.N * 6;
-      for (int idx = et; idx < BM * EDVP; idx += 256) {
+      for (int idx = et; idx < BM * EDVP; idx += E_SM_THREADS) {
         const int r = idx / EDVP, c = idx % EDVP, tok = i0 + r;
         float val = 0.f;
         if (tok < p.N) {
@@ -316,7 +339,7 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       }
       epi_bar2();
       float* out = p.Fpart + ((size_t)g * IT + it) * dv * dv;
-      for (int idx = et; idx < dv * dv; idx += 256) {
+      for (int idx = et; idx < dv * dv; idx += E_SM_THREADS) {
         const int aa = idx / dv, cc = idx % dv;
         float s = 0.f;
 #pragma unroll 8

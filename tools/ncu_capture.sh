@@ -2,7 +2,8 @@
 # ncu captures (run under gpurun, ONE GPU).  Outputs land in gpurun_out/ and are summarised into profiles/.
 #   usage: bash tools/ncu_capture.sh <tag> [full]
 #   launch list of the whole bench command (summarised per steady-state step by tools/summarize_launches.py --last-step)
-#   + with `full`: `--set full` captures of the top kernels (source-level, -lineinfo build).
+#   + with `full`: `--set full` captures of the top kernels (source-level, -lineinfo build).  The .ncu-rep files are
+#   exported to CSV on the box (raw page + SASS source page of one launch) and deleted: gpurun_out/ is capped at 64 MiB.
 set -x
 TAG=${1:-r1}
 mkdir -p gpurun_out
@@ -11,8 +12,19 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-fi
 if [ "$2" == "full" ]; then
   NCU="ncu --set full --clock-control none --import-source on"
   B1="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
-  $NCU -k regex:tc_gemm_kernel -s 60 -c 12 -f -o gpurun_out/${TAG}_tc_gemm $B1 > gpurun_out/ncu_gemm.log 2>&1
-  $NCU -k regex:'tc_emm_pv_kernel|tc_score_kernel' -s 3 -c 4 -f -o gpurun_out/${TAG}_tc_emm $B1 > gpurun_out/ncu_emm.log 2>&1
-  $NCU -k regex:'la_reduce_allheads|la_small_kernel|layernorm_vec_kernel|la_fold_merge|fine_window_gather|linear_simt' -s 30 -c 12 -f -o gpurun_out/${TAG}_hbm_kernels $B1 > gpurun_out/ncu_hbm.log 2>&1
+  export_rep() {  # <name> <launch index for the source page>
+    ncu -i gpurun_out/$1.ncu-rep --page raw --csv > gpurun_out/$1_raw.csv 2>/dev/null
+    ncu -i gpurun_out/$1.ncu-rep --page source --csv --print-source sass --launch-skip $2 --launch-count 1 > gpurun_out/$1_src.csv 2>/dev/null
+    rm -f gpurun_out/$1.ncu-rep
+  }
+  $NCU -k regex:tc_gemm_kernel -s 60 -c 10 -f -o gpurun_out/${TAG}_tc_gemm $B1 > gpurun_out/ncu_gemm.log 2>&1
+  export_rep ${TAG}_tc_gemm 2
+  $NCU -k regex:'tc_emm_pv_kernel' -s 0 -c 1 -f -o gpurun_out/${TAG}_tc_emm_pv $B1 > gpurun_out/ncu_emm.log 2>&1
+  export_rep ${TAG}_tc_emm_pv 0
+  $NCU -k regex:'tc_score_kernel' -s 1 -c 3 -f -o gpurun_out/${TAG}_tc_score $B1 > gpurun_out/ncu_score.log 2>&1
+  export_rep ${TAG}_tc_score 0
+  $NCU -k regex:'la_reduce_allheads|la_small|layernorm_vec_kernel|la_fold_merge|fine_window_gather|fine_match_kernel|match_decide|eightpt|pose_solve' -s 20 -c 14 -f -o gpurun_out/${TAG}_hbm_kernels $B1 > gpurun_out/ncu_hbm.log 2>&1
+  export_rep ${TAG}_hbm_kernels 0
 fi
 ls -la gpurun_out
+du -sh gpurun_out

@@ -9,8 +9,11 @@ import sys
 rep, idx = sys.argv[1], int(sys.argv[2])
 view = sys.argv[3] if len(sys.argv) > 3 else "cuda"
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", view, "--launch-skip", str(idx),
-                      "--launch-count", "1"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):  # exported on the GPU box: ncu -i x.ncu-rep --page source --csv --print-source sass ...
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", view, "--launch-skip",
+                          str(idx), "--launch-count", "1"], capture_output=True, text=True).stdout
 lines = out.splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"') or l.startswith('"#"') or l.startswith('"Line'))
 print(lines[0][:200])
