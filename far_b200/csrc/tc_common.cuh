@@ -55,6 +55,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// One elected lane of a converged warp (CUTLASS' elect_one_sync): the predicate comes from ELECT, so the compiler keeps
+// the guarded tcgen05 / TMA instructions and their descriptor arithmetic on the uniform datapath instead of wrapping
+// every instruction issued under `if (lane == 0)` in an ELECT / BRA.U.ANY loop with R2UR moves (~10 SASS instructions
+// per UTCHMMA: the single issuing thread could not keep 32-64-cycle MMAs back to back).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a warp-uniform value (shuffle broadcast: the compiler's uniformity analysis accepts it)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

@@ -130,7 +130,7 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   float(*Ts)[ETP] = reinterpret_cast<float(*)[ETP]>(gen_st);
   float(*Vs)[ETP] = reinterpret_cast<float(*)[ETP]>(gen_st + (size_t)BM * ETP * 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int it = blockIdx.x, g = blockIdx.y, IT = gridDim.x;
   const int g0 = g % p.H, g1 = g / p.H;
   const int i0 = it * BM;
@@ -192,7 +192,9 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // Whole warp in the (warp-uniform) loop, barrier waits by all lanes, one elected lane issues (tc_common.cuh:
+    // elect_one): UTCHMMA back to back instead of ~10 SASS instructions of ELECT/BRA/R2UR glue per 32-48-cycle MMA.
+    {
       constexpr uint32_t idS = idesc_tf32(BM, EBJ), idT = idesc_tf32(BM, EDVP);
       mbar_wait(q_full, 0);
       tc_fence_after();
@@ -203,24 +205,27 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         // earlier by this same thread and tcgen05.mma instructions of one thread execute in issue order, so the
         // write-after-read on TMEM is ordered by the pipe itself -- and the tensor pipe never drains between tiles.
         tc_fence_after();
-        const uint32_t kbase = st_base + st * E_STAGE;
-        const uint32_t tS_main = tSP(st), tS_cross = tSP(st) + 64;
+        if (elect_one()) {
+          const uint32_t kbase = st_base + st * E_STAGE;
+          const uint32_t tS_main = tSP(st), tS_cross = tSP(st) + 64;
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t dQhi = make_kmajor_sw128_desc(q_base + (kb * 2 + 0) * TILE_BYTES);
-          const uint64_t dQlo = make_kmajor_sw128_desc(q_base + (kb * 2 + 1) * TILE_BYTES);
-          const uint64_t dKhi = make_kmajor_sw128_desc(kbase + (kb * 2 + 0) * E_KT);
-          const uint64_t dKlo = make_kmajor_sw128_desc(kbase + (kb * 2 + 1) * E_KT);
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t dQhi = make_kmajor_sw128_desc(q_base + (kb * 2 + 0) * TILE_BYTES);
+            const uint64_t dQlo = make_kmajor_sw128_desc(q_base + (kb * 2 + 1) * TILE_BYTES);
+            const uint64_t dKhi = make_kmajor_sw128_desc(kbase + (kb * 2 + 0) * E_KT);
+            const uint64_t dKlo = make_kmajor_sw128_desc(kbase + (kb * 2 + 1) * E_KT);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-            umma_tf32(tS_cross, dQlo + koff, dKhi + koff, idS, (kb | k) ? 1u : 0u);
-            umma_tf32(tS_cross, dQhi + koff, dKlo + koff, idS, 1u);
-            umma_tf32(tS_main, dQhi + koff, dKhi + koff, idS, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+              umma_tf32(tS_cross, dQlo + koff, dKhi + koff, idS, (kb | k) ? 1u : 0u);
+              umma_tf32(tS_cross, dQhi + koff, dKlo + koff, idS, 1u);
+              umma_tf32(tS_main, dQhi + koff, dKhi + koff, idS, (kb | k) ? 1u : 0u);
+            }
           }
+          umma_commit(s_full(st));
+          umma_commit(k_empty(st));
         }
-        umma_commit(s_full(st));
-        umma_commit(k_empty(st));
+        __syncwarp();
       };
       issue_S(0);
       if (JT > 1) issue_S(1);
@@ -231,27 +236,30 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         mbar_wait(v_full(st), ph);
         mbar_wait(p_full(st), ph);
         tc_fence_after();
-        const uint32_t vbase = st_base + st * E_STAGE + E_K_STAGE;
-        const uint32_t tP_hi = tSP(st), tP_lo = tSP(st) + 64;
+        if (elect_one()) {
+          const uint32_t vbase = st_base + st * E_STAGE + E_K_STAGE;
+          const uint32_t tP_hi = tSP(st), tP_lo = tSP(st) + 64;
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t dVhi = make_kmajor_sw128_desc(vbase + (kb * 2 + 0) * E_VT);
-          const uint64_t dVlo = make_kmajor_sw128_desc(vbase + (kb * 2 + 1) * E_VT);
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t dVhi = make_kmajor_sw128_desc(vbase + (kb * 2 + 0) * E_VT);
+            const uint64_t dVlo = make_kmajor_sw128_desc(vbase + (kb * 2 + 1) * E_VT);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-            const uint32_t acol = (uint32_t)(kb * BK + k * UMMA_K);
-            const uint32_t first = (jt | kb | k) ? 1u : 0u;
-            umma_tf32_ts(tT_cross, tP_lo + acol, dVhi + koff, idT, first);
-            umma_tf32_ts(tT_cross, tP_hi + acol, dVlo + koff, idT, 1u);
-            umma_tf32_ts(tT_main, tP_hi + acol, dVhi + koff, idT, first);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+              const uint32_t acol = (uint32_t)(kb * BK + k * UMMA_K);
+              const uint32_t first = (jt | kb | k) ? 1u : 0u;
+              umma_tf32_ts(tT_cross, tP_lo + acol, dVhi + koff, idT, first);
+              umma_tf32_ts(tT_cross, tP_hi + acol, dVlo + koff, idT, 1u);
+              umma_tf32_ts(tT_main, tP_hi + acol, dVhi + koff, idT, first);
+            }
           }
+          umma_commit(v_empty(st));   // V' stage reusable
+          if (jt == JT - 1) umma_commit(t_full);
         }
-        umma_commit(v_empty(st));   // V' stage reusable
+        __syncwarp();
         // queue S(jt+2) right behind it (same S/P buffer): the softmax warps work on tile jt+1 meanwhile
         if (jt + 2 < JT) issue_S(jt + 2);
       }
-      umma_commit(t_full);
     }
   } else {
     // ===================== softmax / epilogue: 16 warps, thread = (query row, 16-key group of the j-tile) ========

@@ -94,7 +94,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - raw));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_pg = (p.L + BM - 1) / BM;  // m-tiles per group
   const int num_tiles = p.G * tiles_pg * tiles_n;
@@ -117,7 +117,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {  // whole warp in the loop; one elected lane issues the TMA instructions
       int stage = 0;
       uint32_t phase = 0;
       // L2 prefetch of the raw activation tiles PF k-blocks ahead of the shared-memory ring (cp.async.bulk.prefetch):
@@ -131,19 +131,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         if (kb_p < p.kb1) tma_prefetch_4d(&mapAhi, kb_p * BK, r0_p, g_p, 0);
         else tma_prefetch_4d(&mapAlo, (kb_p - p.kb1) * BK, r0_p, g_p, 0);
       };
-      if (kRawA && !(p.dbg & 64)) {
+      if (kRawA && !(p.dbg & 64) && elect_one()) {
         for (int i = 0; i < PF; ++i) prefetch_a(blockIdx.x + (i / kblocks) * gridDim.x, i % kblocks);
       }
+      __syncwarp();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile / tiles_n, n0 = (tile % tiles_n) * BN;
         const int g = tm / tiles_pg, r0 = (tm % tiles_pg) * BM, gb = p.b_grouped ? g : 0;
         for (int kb = 0; kb < kblocks; ++kb) {
-          if (kRawA && !(p.dbg & 64)) {
-            const int ahead = kb + PF;
-            prefetch_a(tile + (ahead / kblocks) * gridDim.x, ahead % kblocks);
+          if (kRawA && !(p.dbg & 64)) {   // issued before the (possibly long) wait for a free stage
+            if (elect_one()) {
+              const int ahead = kb + PF;
+              prefetch_a(tile + (ahead / kblocks) * gridDim.x, ahead % kblocks);
+            }
+            __syncwarp();
           }
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sbase = base + stage * STAGE_BYTES;
+          if (elect_one()) {
           if (kRawA && (p.dbg & 24)) {  // diagnostics: 8 = skip the B loads, 16 = skip the A load
             mbar_arrive_expect_tx(full_bar(stage), ((p.dbg & 8) ? 0 : 2 * TILE_BYTES) + ((p.dbg & 16) ? 0 : TILE_BYTES));
             if (!(p.dbg & 16)) tma_load_4d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, r0, g, 0);
@@ -151,10 +156,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
               tma_load_4d(sbase + 2 * TILE_BYTES, &mapBhi, full_bar(stage), kb * BK, n0, gb, 0);
               tma_load_4d(sbase + 3 * TILE_BYTES, &mapBlo, full_bar(stage), kb * BK, n0, gb, 0);
             }
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            continue;
-          }
-          if (kRawA) {
+          } else if (kRawA) {
             mbar_arrive_expect_tx(full_bar(stage), 3 * TILE_BYTES);
             if (kb < p.kb1) tma_load_4d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, r0, g, 0);
             else tma_load_4d(sbase + 0 * TILE_BYTES, &mapAlo, full_bar(stage), (kb - p.kb1) * BK, r0, g, 0);
@@ -163,15 +165,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             tma_load_4d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, r0, g, 0);
             tma_load_4d(sbase + 1 * TILE_BYTES, &mapAlo, full_bar(stage), kb * BK, r0, g, 0);
           }
-          tma_load_4d(sbase + 2 * TILE_BYTES, &mapBhi, full_bar(stage), kb * BK, n0, gb, 0);
-          tma_load_4d(sbase + 3 * TILE_BYTES, &mapBlo, full_bar(stage), kb * BK, n0, gb, 0);
+          if (!(kRawA && (p.dbg & 24))) {
+            tma_load_4d(sbase + 2 * TILE_BYTES, &mapBhi, full_bar(stage), kb * BK, n0, gb, 0);
+            tma_load_4d(sbase + 3 * TILE_BYTES, &mapBlo, full_bar(stage), kb * BK, n0, gb, 0);
+          }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) loop and waits on the barriers; one elected lane issues the MMAs and
+    // the commits, so descriptors and loop state stay in uniform registers.
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -187,22 +195,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(kRawA ? conv_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sbase = base + stage * STAGE_BYTES;
-          const uint64_t dAhi = make_kmajor_sw128_desc(sbase + 0 * TILE_BYTES);
-          const uint64_t dAlo = make_kmajor_sw128_desc(sbase + 1 * TILE_BYTES);
-          const uint64_t dBhi = make_kmajor_sw128_desc(sbase + 2 * TILE_BYTES);
-          const uint64_t dBlo = make_kmajor_sw128_desc(sbase + 3 * TILE_BYTES);
+          if (elect_one()) {
+            const uint32_t sbase = base + stage * STAGE_BYTES;
+            const uint64_t dAhi = make_kmajor_sw128_desc(sbase + 0 * TILE_BYTES);
+            const uint64_t dAlo = make_kmajor_sw128_desc(sbase + 1 * TILE_BYTES);
+            const uint64_t dBhi = make_kmajor_sw128_desc(sbase + 2 * TILE_BYTES);
+            const uint64_t dBlo = make_kmajor_sw128_desc(sbase + 3 * TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < ((p.dbg & 4) ? 0 : BK / UMMA_K); ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128-byte swizzle row
-            umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
-            umma_tf32(tmem_small, dAhi + koff, dBlo + koff, kIdescTf32, 1u);
-            umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (p.dbg & 4) break;
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128-byte swizzle row
+              umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+              umma_tf32(tmem_small, dAhi + koff, dBlo + koff, kIdescTf32, 1u);
+              umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+            if (kb == kblocks - 1) umma_commit(tfull_bar(acc));  // accumulator complete
           }
-          umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));      // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }

@@ -73,7 +73,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
   float(*scr)[SPITCH] = reinterpret_cast<float(*)[SPITCH]>(gen);
   float* cls2 = reinterpret_cast<float*>(gen + (size_t)BM * SPITCH * 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int IT = (p.L + BM - 1) / BM, JT = (p.S + BN - 1) / BN;
   const int num_tiles = p.G * IT * JT;
   const int kblocks = (p.K + BK - 1) / BK;
@@ -94,7 +94,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // whole warp in the loop; one elected lane issues the TMA instructions
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -102,18 +102,21 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
         const int g0 = g % p.H, g1 = g / p.H;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sbase = base + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-          tma_load_4d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, it * BM, g0, g1);
-          tma_load_4d(sbase + 1 * TILE_BYTES, &mapAlo, full_bar(stage), kb * BK, it * BM, g0, g1);
-          tma_load_4d(sbase + 2 * TILE_BYTES, &mapBhi, full_bar(stage), kb * BK, jt * BN, g0, g1);
-          tma_load_4d(sbase + 3 * TILE_BYTES, &mapBlo, full_bar(stage), kb * BK, jt * BN, g0, g1);
+          if (elect_one()) {
+            const uint32_t sbase = base + stage * STAGE_BYTES;
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_4d(sbase + 0 * TILE_BYTES, &mapAhi, full_bar(stage), kb * BK, it * BM, g0, g1);
+            tma_load_4d(sbase + 1 * TILE_BYTES, &mapAlo, full_bar(stage), kb * BK, it * BM, g0, g1);
+            tma_load_4d(sbase + 2 * TILE_BYTES, &mapBhi, full_bar(stage), kb * BK, jt * BN, g0, g1);
+            tma_load_4d(sbase + 3 * TILE_BYTES, &mapBlo, full_bar(stage), kb * BK, jt * BN, g0, g1);
+          }
+          __syncwarp();
           if (++stage == S_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp in the loop, one elected lane issues the MMAs (tc_common.cuh: elect_one)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -126,22 +129,25 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sbase = base + stage * STAGE_BYTES;
-          const uint64_t dAhi = make_kmajor_sw128_desc(sbase + 0 * TILE_BYTES);
-          const uint64_t dAlo = make_kmajor_sw128_desc(sbase + 1 * TILE_BYTES);
-          const uint64_t dBhi = make_kmajor_sw128_desc(sbase + 2 * TILE_BYTES);
-          const uint64_t dBlo = make_kmajor_sw128_desc(sbase + 3 * TILE_BYTES);
+          if (elect_one()) {
+            const uint32_t sbase = base + stage * STAGE_BYTES;
+            const uint64_t dAhi = make_kmajor_sw128_desc(sbase + 0 * TILE_BYTES);
+            const uint64_t dAlo = make_kmajor_sw128_desc(sbase + 1 * TILE_BYTES);
+            const uint64_t dBhi = make_kmajor_sw128_desc(sbase + 2 * TILE_BYTES);
+            const uint64_t dBlo = make_kmajor_sw128_desc(sbase + 3 * TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-            umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
-            umma_tf32(tmem_small, dAhi + koff, dBlo + koff, kIdescTf32, 1u);
-            umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+              umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+              umma_tf32(tmem_small, dAhi + koff, dBlo + koff, kIdescTf32, 1u);
+              umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));
+            if (kb == kblocks - 1) umma_commit(tfull_bar(acc));
           }
-          umma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == S_STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
