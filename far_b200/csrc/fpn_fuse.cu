@@ -70,6 +70,85 @@ __global__ void __launch_bounds__(256) scale_shift_act_nhwc_kernel(float4* __res
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backbone stem: conv1 (7x7, stride 2, padding 3, ONE input channel -> 128) + folded BatchNorm + ReLU
+// (resnet_fpn.py:52-54,80: `x0 = relu(bn1(conv1(x)))`), written NHWC.  cuDNN has no tensor-core engine for C_in = 1:
+// it ran a generic fp32 kernel (3.2 ms for 64 images) plus separate bias and ReLU passes over the 2.5 GB output.
+// Weights in REGISTERS, inputs by broadcast: a lane owns one output channel (its 49 taps live in registers), a warp
+// owns 32 channels of one output row and walks it 8 pixels at a time; per kernel row the 21 input values those 8
+// pixels need are six warp-uniform LDS.128 (one wavefront each) feeding 56 FMAs per lane -- shared-memory traffic is
+// ~0.1 wavefront per FMA instruction (a version with the weights in shared memory was LSU-bound at 0.4).  Each store
+// instruction writes 128 contiguous bytes of an NHWC pixel.
+constexpr int ST_TH = 2, ST_TW = 64, ST_C = 128, ST_K = 7, ST_PX = 8;
+constexpr int ST_PH = 2 * ST_TH + 5, ST_PW = 2 * ST_TW + 5, ST_PP = 2 * ST_TW + 8 + 8;  // 9 x 133 patch, pitch 144
+
+// wt: weights pre-transposed to [49][128] (tap-major: coalesced per-lane weight loads).
+// grid (x tiles, y chunks, N); block 256 = 2 rows x 4 channel quarters; a CTA walks `tiles_per_cta` 2-row tiles down.
+__global__ void __launch_bounds__(256, 2) stem_conv7x7s2_relu_kernel(const float* __restrict__ x,
+                                                                      const float* __restrict__ wt,
+                                                                      const float* __restrict__ bias,
+                                                                      float* __restrict__ y, int H, int W, int OH,
+                                                                      int OW, int tiles_per_cta) {
+  __shared__ __align__(16) float patch[ST_PH][ST_PP];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int ch = (warp & 3) * 32 + lane, row = warp >> 2;
+  const int n = blockIdx.z, ox0 = blockIdx.x * ST_TW;
+  float wreg[ST_K * ST_K];
+#pragma unroll
+  for (int i = 0; i < ST_K * ST_K; ++i) wreg[i] = __ldg(wt + i * ST_C + ch);
+  const float b = __ldg(bias + ch);
+  const float* xin = x + (size_t)n * H * W;
+  const int ix0 = 2 * ox0 - 3;
+  for (int ty = 0; ty < tiles_per_cta; ++ty) {
+    const int oy0 = (blockIdx.y * tiles_per_cta + ty) * ST_TH;
+    if (oy0 >= OH) break;
+    const int iy0 = 2 * oy0 - 3;
+    __syncthreads();  // previous tile's reads of `patch` are done
+    for (int idx = t; idx < ST_PH * ST_PP; idx += 256) {
+      const int r = idx / ST_PP, c = idx % ST_PP;
+      const int iy = iy0 + r, ix = ix0 + c;
+      patch[r][c] = (c < ST_PW + 3 && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xin + (size_t)iy * W + ix) : 0.f;
+    }
+    __syncthreads();
+    const int oy = oy0 + row;
+#pragma unroll 1
+    for (int xc = 0; xc < ST_TW / ST_PX; ++xc) {
+      float acc[ST_PX];
+#pragma unroll
+      for (int i = 0; i < ST_PX; ++i) acc[i] = b;
+#pragma unroll
+      for (int ky = 0; ky < ST_K; ++ky) {
+        // inputs of 8 consecutive output pixels for this kernel row: patch columns [16 xc, 16 xc + 21)
+        const float4* pr = reinterpret_cast<const float4*>(&patch[2 * row + ky][2 * ST_PX * xc]);
+        float in[24];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const float4 v = pr[q];
+          in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int kx = 0; kx < ST_K; ++kx)
+#pragma unroll
+          for (int i = 0; i < ST_PX; ++i) acc[i] = fmaf(in[2 * i + kx], wreg[ky * ST_K + kx], acc[i]);
+      }
+      if (oy < OH) {
+#pragma unroll
+        for (int i = 0; i < ST_PX; ++i) {
+          const int ox = ox0 + xc * ST_PX + i;
+          if (ox < OW) __stcs(y + (((size_t)n * OH + oy) * OW + ox) * ST_C + ch, fmaxf(acc[i], 0.f));
+        }
+      }
+    }
+  }
+}
+
+// w [Cout][49] -> wt [49][Cout]
+__global__ void stem_weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < Cout * 49) wt[(idx % 49) * Cout + idx / 49] = w[idx];
+}
+
 }  // namespace far
 
 using namespace far;
@@ -107,6 +186,30 @@ extern "C" int far_scale_shift_act_nhwc(float* x, const float* scale, const floa
   scale_shift_act_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(scale), reinterpret_cast<const float4*>(shift),
       total, C / 4, negative_slope);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+extern "C" size_t far_stem_conv_workspace_bytes(int Cout) { return (size_t)Cout * 49 * sizeof(float) + 256; }
+
+extern "C" int far_stem_conv7x7s2_relu_nhwc(const float* x, const float* w, const float* bias, float* y, int N, int H,
+                                            int W, int Cout, float* workspace, size_t workspace_bytes, void* stream) {
+  if (N <= 0) return FAR_OK;
+  if (x == nullptr || w == nullptr || bias == nullptr || y == nullptr || H < 1 || W < 1 || Cout != ST_C) return FAR_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(workspace)) & 15u)
+    return FAR_ERR_ARG;
+  if (workspace == nullptr || workspace_bytes < far_stem_conv_workspace_bytes(Cout)) return FAR_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  stem_weight_transpose_kernel<<<ceil_div(Cout * 49, 256), 256, 0, st>>>(w, workspace, Cout);
+  FAR_CHECK_LAUNCH();
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;   // floor((H + 2*3 - 7) / 2) + 1
+  const int ytiles = ceil_div(OH, ST_TH), xtiles = ceil_div(OW, ST_TW);
+  // enough CTAs for ~8 waves of 2 CTAs/SM, each walking several tiles with the weights resident
+  int tiles_per_cta = 1;
+  while (tiles_per_cta < ytiles && (long long)xtiles * ceil_div(ytiles, tiles_per_cta * 2) * N >= 16LL * kNumSMs) tiles_per_cta *= 2;
+  dim3 grid(xtiles, ceil_div(ytiles, tiles_per_cta), N);
+  ProfScope prof(PROF_FPN, 2.0 * N * OH * OW * ST_C * 49, 4.0 * ((double)N * H * W + (double)N * OH * OW * ST_C), st);
+  stem_conv7x7s2_relu_kernel<<<grid, 256, 0, st>>>(x, workspace, bias, y, H, W, OH, OW, tiles_per_cta);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }

@@ -111,6 +111,7 @@ class ResNetFPN_8_2(nn.Module):
                     f[(li, bi, 2)] = fold(blk.conv2, blk.bn2)
                     if blk.downsample is not None:
                         f[(li, bi, "d")] = fold(blk.downsample[0], blk.downsample[1])
+                        f[(li, bi, "2d")] = (f[(li, bi, 2)][1] + f[(li, bi, "d")][1]).contiguous()
             f["o2"] = affine(self.layer2_outconv2[1])
             f["o1"] = affine(self.layer1_outconv2[1])
         self._fold_cache = (key, f)
@@ -127,12 +128,18 @@ class ResNetFPN_8_2(nn.Module):
             w2, b2 = f[(li, bi, 2)]
             y = torch.cudnn_convolution_relu(x, w1, b1, stride, pad1, one, 1)
             if blk.downsample is not None:
+                # relu(conv2(y) + b2 + (conv_d(x) + b_d)): the downsample bias rides on conv2's bias, so the 1x1
+                # stride-2 conv needs no separate bias pass over its output
                 wd, bd = f[(li, bi, "d")]
-                x = F.conv2d(x, wd, bd, stride=stride)
+                x = F.conv2d(x, wd, None, stride=stride)
+                b2 = f[(li, bi, "2d")]
             return torch.cudnn_convolution_add_relu(y, w2, x, 1.0, b2, one, pad1, one, 1)
 
         w, b = f["stem"]
-        x0 = torch.relu_(F.conv2d(x, w, b, stride=2, padding=3))   # C_in = 1: not a fused-engine shape
+        if w.shape[0] == 128 and x.shape[1] == 1:
+            x0 = ops.stem_conv7x7s2_relu(x, w, b)      # hand kernel: conv + bias + ReLU in one pass, NHWC out
+        else:
+            x0 = torch.relu_(F.conv2d(x, w, b, stride=2, padding=3))   # C_in = 1: not a fused-engine shape
         feats = []
         cur = x0
         for li, layer in enumerate((self.layer1, self.layer2, self.layer3)):

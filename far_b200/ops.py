@@ -142,6 +142,24 @@ def upsample2x_add(low, skip=None):
     return out.permute(0, 3, 1, 2)
 
 
+def stem_conv7x7s2_relu(x, weight, bias):
+    """relu(conv2d(x, weight, stride=2, padding=3) + bias) for the 1-channel 7x7 stem (resnet_fpn.py:52-54,80, BN
+    folded).  x [N,1,H,W] -> channels_last [N,128,OH,OW]."""
+    lib = L.load()
+    n, c, h, w = x.shape
+    if c != 1 or tuple(weight.shape[1:]) != (1, 7, 7):
+        raise L.FarError("stem_conv7x7s2_relu: needs a 1-channel input and a [Cout,1,7,7] kernel")
+    cout = weight.shape[0]
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    out = torch.empty((n, oh, ow, cout), dtype=torch.float32, device=x.device)
+    ws = _ws(lib.far_stem_conv_workspace_bytes(cout), x.device)
+    with _timed("far_stem_conv7x7s2_relu_nhwc"):
+        check(lib.far_stem_conv7x7s2_relu_nhwc(ptr(f32c(x)), ptr(f32c(weight).reshape(cout, 49)), ptr(f32c(bias)),
+                                               ptr(out), n, h, w, cout, ptr(ws), ws.numel(), stream()),
+              "far_stem_conv7x7s2_relu_nhwc")
+    return out.permute(0, 3, 1, 2)
+
+
 def scale_shift_act_(x, scale, shift, negative_slope):
     """In place leaky_relu(x*scale[c] + shift[c]) on a channels_last [N,C,H,W] map (eval BatchNorm2d + LeakyReLU,
     resnet_fpn.py:84-95)."""

@@ -91,6 +91,13 @@ int far_upsample2x_add_nhwc(const float* low, const float* skip, float* out, int
  * (resnet_fpn.py:84-95 layer{1,2}_outconv2).  scale may be NULL (bias only).  x:[pixels, C] NHWC, C % 4 == 0. */
 int far_scale_shift_act_nhwc(float* x, const float* scale, const float* shift, long long pixels, int C,
                              float negative_slope, void* stream);
+/* Backbone stem: y = relu(conv2d(x, w, stride 2, padding 3) + bias) for a ONE-channel input and a 7x7 kernel,
+ * x:[N,1,H,W] fp32, w:[Cout,1,7,7] (eval BatchNorm folded in), y:[N,OH,OW,Cout] NHWC, Cout == 128.
+ * Replaces `self.relu(self.bn1(self.conv1(x)))` (mp3d_loftr/src/loftr/backbone/resnet_fpn.py:52-54,80); cuDNN has no
+ * tensor-core engine for C_in = 1.  Exact fp32 FMA arithmetic. */
+size_t far_stem_conv_workspace_bytes(int Cout);
+int far_stem_conv7x7s2_relu_nhwc(const float* x, const float* w, const float* bias, float* y, int N, int H, int W,
+                                 int Cout, float* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- LinearAttention.forward (mp3d_loftr/src/loftr/loftr_module/linear_attention.py:20-52) -----------
  * q:[N,L,H*D], k,v:[N,S,H*D] (row strides ldq/ldk/ldv), out:[N,L,H*D] (ld ldo).

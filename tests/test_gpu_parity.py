@@ -557,3 +557,17 @@ def test_backbone_fused_eval_matches_module_graph():
         c1, f1 = m(x)
     assert_close(c1, c0, 2e-4, 2e-4, "fused backbone coarse")
     assert_close(f1, f0, 2e-4, 2e-4, "fused backbone fine")
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 480, 640), (1, 96, 128), (3, 37, 51)])
+def test_stem_conv7x7s2_relu(n, h, w):
+    """Hand-written backbone stem (7x7 / stride 2 / 1 -> 128 channels + folded BN + ReLU, NHWC out) against
+    F.conv2d in fp32 (exact FMA arithmetic on both sides up to summation order)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(n, 1, h, w, generator=g)
+    wt = torch.randn(128, 1, 7, 7, generator=g) * 0.2
+    b = torch.randn(128, generator=g) * 0.1
+    ref = torch.relu(torch.nn.functional.conv2d(x.double(), wt.double(), b.double(), stride=2, padding=3))
+    out = ops.stem_conv7x7s2_relu(cu(x), cu(wt), cu(b))
+    assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+    assert_close(out, ref, 2e-5, 1e-5, "stem conv")
