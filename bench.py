@@ -259,8 +259,10 @@ def run_far(args, rank, world, local_rank):
                 "traffic": tr["dram_bytes_per_launch"] if tr else None,
                 "traffic_source": tr["source"] if tr else None,
                 "share_of_step": kshare.get(name),
+                "frac_of_3xtf32_ceiling": (achieved / (peak / 6.0)) if tensor_bound else None,
                 "note": "3xTF32 error-compensated fp32 GEMM: 3 tensor-core MMAs per algorithmic FMA, so frac <= 1/3 of "
-                        "the tf32 pipe (= 1/6 of the bf16 peak used as denominator)" if tensor_bound else None}
+                        "the tf32 pipe (= 1/6 of the bf16 peak used as denominator); traffic = mean DRAM bytes per "
+                        "launch over one steady-state step (profiles/ncu_traffic.json)" if tensor_bound else None}
     line = {"metric": "image-pairs/sec @640x480", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -24,7 +24,7 @@ __host__ __device__ inline int score_tiles_j(int S) { return ceil_div(S, TBN); }
 // workspace (floats) needed by score_lse: row partials + col partials.  The tcgen05 kernels emit two partials per
 // 128-wide tile and direction (64-column / 64-row halves), so the scratch is sized for 2*JT and 2*IT.
 inline size_t score_lse_scratch_floats(int G, int L, int S) {
-  return (size_t)G * 2 * score_tiles_j(S) * L * 2 + (size_t)G * 2 * score_tiles_i(L) * S * 2;
+  return (size_t)G * 2 * score_tiles_j(S) * L * 2 + (size_t)G * 4 * score_tiles_i(L) * S * 2;  // (K = 64 kernel: 4 column partials per tile)
 }
 
 // Computes row_lse [G][L] and col_lse [G][S].  `scratch` >= score_lse_scratch_floats().

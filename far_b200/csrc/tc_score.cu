@@ -264,6 +264,211 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// LSE pass for K = 64 (the EMM head dimension): query-tile-resident streaming kernel.
+// tc_score_kernel gives every 128x128 tile the whole 2-stage ring when K = 64 (2 k-blocks), so the next tile's loads
+// cannot start before the current tile's MMAs retire (31 % tensor-pipe activity, ncu).  Here a CTA owns one 128-query
+// tile of one (batch, head): Q (hi | lo, 64 KB) is loaded once, the 128-key K tiles stream through a 2-deep ring of
+// whole tiles, S is double-buffered in TMEM (2 x (main | cross) x 128 columns).  Epilogue warps own rows: the row
+// (max, sum) is carried online in registers across all key tiles (one pair per row and 64-column half at the end);
+// column statistics are taken per warp (32 rows) through a warp-private 32x33 transpose -- no block-level barrier
+// anywhere in the epilogue -- and written as 4 partials per query tile.
+constexpr int L_THREADS = 64 + 256;
+constexpr int L_Q_BYTES = 4 * TILE_BYTES;
+constexpr int L_K_STAGE = 4 * TILE_BYTES;
+constexpr int L_SCR_BYTES = 8 * 32 * 33 * 4;
+constexpr size_t LSE64_SMEM = 1024 + L_Q_BYTES + 2 * L_K_STAGE + L_SCR_BYTES + 256;
+
+struct Lse64Args {
+  int G, H, N, S;        // groups, heads per batch, query rows, key rows
+  float scale2;
+  float2* rowpart;       // [(g*2 + half)*N + i]
+  float2* colpart;       // [(g*4*IT + 4*it + quarter)*S + j]
+};
+
+__global__ void __launch_bounds__(L_THREADS, 1)
+tc_lse64_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant__ CUtensorMap mapQlo,
+                const __grid_constant__ CUtensorMap mapKhi, const __grid_constant__ CUtensorMap mapKlo, Lse64Args p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t q_base = base, k_base = base + L_Q_BYTES;
+  const uint32_t scr_base = k_base + 2 * L_K_STAGE;
+  const uint32_t bar_base = scr_base + L_SCR_BYTES;
+  const uint32_t q_full = bar_base;
+  auto k_full = [&](int s) { return bar_base + 8u + 8u * s; };
+  auto k_empty = [&](int s) { return bar_base + 24u + 8u * s; };
+  auto tfull_bar = [&](int s) { return bar_base + 40u + 8u * s; };
+  auto tempty_bar = [&](int s) { return bar_base + 56u + 8u * s; };
+  const uint32_t tmem_slot = bar_base + 72u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - raw));
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int it = blockIdx.x, g = blockIdx.y, IT = gridDim.x;
+  const int g0 = g % p.H, g1 = g / p.H;
+  const int i0 = it * BM;
+  const int JT = (p.S + BN - 1) / BN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, L_Q_BYTES);
+      for (int kb = 0; kb < 2; ++kb) {
+        tma_load_4d(q_base + (kb * 2 + 0) * TILE_BYTES, &mapQhi, q_full, kb * BK, i0, g0, g1);
+        tma_load_4d(q_base + (kb * 2 + 1) * TILE_BYTES, &mapQlo, q_full, kb * BK, i0, g0, g1);
+      }
+    }
+    __syncwarp();
+    for (int jt = 0; jt < JT; ++jt) {
+      const int st = jt & 1;
+      mbar_wait(k_empty(st), (uint32_t)(((jt >> 1) & 1) ^ 1));
+      if (elect_one()) {
+        const uint32_t kb_s = k_base + st * L_K_STAGE;
+        mbar_arrive_expect_tx(k_full(st), L_K_STAGE);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_4d(kb_s + (kb * 2 + 0) * TILE_BYTES, &mapKhi, k_full(st), kb * BK, jt * BN, g0, g1);
+          tma_load_4d(kb_s + (kb * 2 + 1) * TILE_BYTES, &mapKlo, k_full(st), kb * BK, jt * BN, g0, g1);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    mbar_wait(q_full, 0);
+    for (int jt = 0; jt < JT; ++jt) {
+      const int st = jt & 1;
+      const uint32_t ph = (uint32_t)((jt >> 1) & 1);
+      mbar_wait(k_full(st), ph);
+      mbar_wait(tempty_bar(st), ph ^ 1u);   // accumulator buffer jt & 1 drained by the epilogue of tile jt - 2
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t kb_s = k_base + st * L_K_STAGE;
+        const uint32_t t_main = tmem_base + (uint32_t)(st * 2 * BN), t_cross = t_main + (uint32_t)BN;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t dQhi = make_kmajor_sw128_desc(q_base + (kb * 2 + 0) * TILE_BYTES);
+          const uint64_t dQlo = make_kmajor_sw128_desc(q_base + (kb * 2 + 1) * TILE_BYTES);
+          const uint64_t dKhi = make_kmajor_sw128_desc(kb_s + (kb * 2 + 0) * TILE_BYTES);
+          const uint64_t dKlo = make_kmajor_sw128_desc(kb_s + (kb * 2 + 1) * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+            umma_tf32(t_cross, dQlo + koff, dKhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+            umma_tf32(t_cross, dQhi + koff, dKlo + koff, kIdescTf32, 1u);
+            umma_tf32(t_main, dQhi + koff, dKhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+          }
+        }
+        umma_commit(k_empty(st));
+        umma_commit(tfull_bar(st));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: 8 warps; thread = (query row, 64-key half) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane, grow = i0 + row;
+    const bool rvalid = grow < p.N;
+    float(*scr)[33] = reinterpret_cast<float(*)[33]>(smem_dyn + (scr_base - raw) + (size_t)ew * 32 * 33 * 4);
+    float m_run = -INFINITY, s_run = 0.f;
+    for (int jt = 0; jt < JT; ++jt) {
+      const int st = jt & 1;
+      const int j0 = jt * BN;
+      mbar_wait(tfull_bar(st), (uint32_t)((jt >> 1) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
+        const int col0 = j0 + c * 32;
+        uint32_t a[32], b[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(st * 2 * BN + c * 32);
+        tmem_ld32_nowait2(taddr, a);
+        tmem_ld32_nowait2(taddr + (uint32_t)BN, b);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (cc == 1) {   // this warp's part of the accumulator is in registers: hand the buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(st));
+        }
+        float x[32];
+        if (rvalid && col0 + 32 <= p.S) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) x[e] = (__uint_as_float(a[e]) + __uint_as_float(b[e])) * p.scale2;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            x[e] = (rvalid && col0 + e < p.S) ? (__uint_as_float(a[e]) + __uint_as_float(b[e])) * p.scale2 : -INFINITY;
+        }
+        // ---- row statistics, online across key tiles (4 independent chains: 2 warps per scheduler need the ILP)
+        float c0 = fmaxf(x[0], x[4]), c1 = fmaxf(x[1], x[5]), c2 = fmaxf(x[2], x[6]), c3 = fmaxf(x[3], x[7]);
+#pragma unroll
+        for (int e = 8; e < 32; e += 4) {
+          c0 = fmaxf(c0, x[e]); c1 = fmaxf(c1, x[e + 1]); c2 = fmaxf(c2, x[e + 2]); c3 = fmaxf(c3, x[e + 3]);
+        }
+        const float m_new = fmaxf(m_run, fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)));
+        if (m_new > -INFINITY) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            a0 += ex2(x[e] - m_new); a1 += ex2(x[e + 1] - m_new); a2 += ex2(x[e + 2] - m_new); a3 += ex2(x[e + 3] - m_new);
+          }
+          s_run = s_run * ex2(m_run - m_new) + ((a0 + a1) + (a2 + a3));
+          m_run = m_new;
+        }
+        // ---- column statistics of this warp's 32 rows: warp-private transpose
+#pragma unroll
+        for (int e = 0; e < 32; ++e) scr[lane][e] = x[e];
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; ++r) x[r] = scr[r][lane];
+        c0 = fmaxf(x[0], x[4]); c1 = fmaxf(x[1], x[5]); c2 = fmaxf(x[2], x[6]); c3 = fmaxf(x[3], x[7]);
+#pragma unroll
+        for (int r = 8; r < 32; r += 4) {
+          c0 = fmaxf(c0, x[r]); c1 = fmaxf(c1, x[r + 1]); c2 = fmaxf(c2, x[r + 2]); c3 = fmaxf(c3, x[r + 3]);
+        }
+        const float cmx = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
+        float cs = 0.f;
+        if (cmx > -INFINITY) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; r += 4) {
+            a0 += ex2(x[r] - cmx); a1 += ex2(x[r + 1] - cmx); a2 += ex2(x[r + 2] - cmx); a3 += ex2(x[r + 3] - cmx);
+          }
+          cs = (a0 + a1) + (a2 + a3);
+        }
+        const int col = col0 + lane;
+        if (col < p.S) p.colpart[((size_t)g * 4 * IT + 4 * it + quarter) * p.S + col] = make_float2(cmx, cs);
+        __syncwarp();   // the next chunk overwrites scr
+      }
+    }
+    if (rvalid) p.rowpart[((size_t)g * 2 + half) * p.N + grow] = make_float2(m_run, s_run);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // hi/lo split of a strided operand set: copies group (b,h) rows [rows x K] into dense [G][rows][K] arrays
 __global__ void split_groups_kernel(const float* __restrict__ x, long long sb, long long sh, int ld, int H, int G,
                                     int rows, int K, float* __restrict__ hi, float* __restrict__ lo) {
@@ -351,6 +556,28 @@ int tc_score_lse_partials(const ScoreArgs& a, float2* rowpart, float2* colpart, 
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   ProfScope prof(PROF_TC_SCORE, 2.0 * a.G * a.L * a.S * a.K, 4.0 * a.G * ((double)a.L + a.S) * a.K, st);
   tc_score_kernel<MODE_LSE><<<grid, S_THREADS, SCORE_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+bool tc_lse64_supported(const ScoreArgs& a) { return tc_score_supported(a) && a.K == 64 && getenv("FAR_LSE64_OFF") == nullptr; }
+
+// row partials: 2 per row ([(g*2 + half)*L + i]); column partials: 4 per 128-query tile ([(g*4*IT + 4*it + q)*S + j])
+int tc_lse64_partials(const ScoreArgs& a, float2* rowpart, float2* colpart, float* ws, size_t ws_bytes, int split_done,
+                      cudaStream_t st) {
+  using namespace tc;
+  SplitOps o;
+  CUtensorMap maps[4];
+  int rc = prepare_operands(a, ws, ws_bytes, &o, maps, split_done, st);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(tc_lse64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LSE64_SMEM);
+    attr = true;
+  }
+  Lse64Args p{a.G, a.H, a.L, a.S, a.scale * kLog2e, rowpart, colpart};
+  ProfScope prof(PROF_TC_SCORE, 2.0 * a.G * a.L * a.S * a.K, 4.0 * a.G * ((double)a.L + a.S) * a.K, st);
+  tc_lse64_kernel<<<dim3(ceil_div(a.L, BM), a.G), L_THREADS, LSE64_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }

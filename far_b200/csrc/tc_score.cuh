@@ -8,6 +8,10 @@ size_t tc_score_workspace_bytes(int G, int L, int S, int K);
 // `split_done` != 0: the workspace already holds the hi/lo split of exactly these operands (skip the split pass).
 int tc_score_lse_partials(const ScoreArgs& a, float2* rowpart, float2* colpart, float* ws, size_t ws_bytes,
                           int split_done, cudaStream_t st);
+// K = 64 (EMM) streaming variant: 2 row partials per row, 4 column partials per 128-row tile (tc_score.cu).
+bool tc_lse64_supported(const ScoreArgs& a);
+int tc_lse64_partials(const ScoreArgs& a, float2* rowpart, float2* colpart, float* ws, size_t ws_bytes, int split_done,
+                      cudaStream_t st);
 int tc_match_conf(const ScoreArgs& a, const float* rowlse, const float* collse, float2* rowmax, float* colmax,
                   float* conf_out, float* ws, size_t ws_bytes, int split_done, cudaStream_t st);
 // Pointers of the dense [G][rows][K] hi/lo operand arrays inside a workspace filled by the passes above.

@@ -9,6 +9,11 @@ TAG=${1:-r1}
 mkdir -p gpurun_out
 B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_${TAG}.csv $B > gpurun_out/ncu_launches_${TAG}.log 2>&1
+# DRAM traffic of every launch of OUR kernels in a steady-state step (single-pass counters, same metrics the full set
+# reports): bench.py's roofline.traffic is the per-launch mean over exactly the launches its `achieved` averages over.
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+    -k regex:'tc_|la_|layernorm|fine_|match_|stem_|eightpt|pose_|emm_|linear_simt|split|lse_|upsample2x|scale_shift|pos_flatten' \
+    -c 3000 --csv --log-file gpurun_out/traffic_${TAG}.csv $B > gpurun_out/ncu_traffic_${TAG}.log 2>&1
 if [ "$2" == "full" ]; then
   NCU="ncu --set full --clock-control none --import-source on"
   B1="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
