@@ -189,27 +189,32 @@ __global__ void __launch_bounds__(32 * H) la_small_allheads_kernel(const float* 
   }
   __syncthreads();
   constexpr int G = 32 / D;      // d-groups per warp (D=16 -> 2)
-  constexpr int ND = D / G;      // d's per lane
+  constexpr int ND = D / G;      // d's per lane: the CONTIGUOUS block [g*ND, g*ND + ND) -> two broadcast LDS.128 per token
+  static_assert(ND == 8, "la_small_allheads_kernel is written for D = 16");
   const int e = lane % D, g = lane / D, hb = h * D;
   float kv[ND], ks[ND];
 #pragma unroll
   for (int i = 0; i < ND; ++i) { kv[i] = 0.f; ks[i] = 0.f; }
   for (int s0 = 0; s0 < S; ++s0) {
     const float ve = sm[2][s0][hb + e];
+    const float4 ka = *reinterpret_cast<const float4*>(&sm[1][s0][hb + g * ND]);
+    const float4 kb = *reinterpret_cast<const float4*>(&sm[1][s0][hb + g * ND + 4]);
+    const float kd[ND] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
 #pragma unroll
     for (int i = 0; i < ND; ++i) {
-      const float kd = sm[1][s0][hb + g + i * G];
-      kv[i] = fmaf(kd, ve, kv[i]);
-      ks[i] += kd;
+      kv[i] = fmaf(kd[i], ve, kv[i]);
+      ks[i] += kd[i];
     }
   }
   for (int l = 0; l < L; ++l) {
+    const float4 qa = *reinterpret_cast<const float4*>(&sm[0][l][hb + g * ND]);
+    const float4 qb = *reinterpret_cast<const float4*>(&sm[0][l][hb + g * ND + 4]);
+    const float qd[ND] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
     float num = 0.f, den = 0.f;
 #pragma unroll
     for (int i = 0; i < ND; ++i) {
-      const float qd = sm[0][l][hb + g + i * G];
-      num = fmaf(qd, kv[i], num);
-      den = fmaf(qd, ks[i], den);
+      num = fmaf(qd[i], kv[i], num);
+      den = fmaf(qd[i], ks[i], den);
     }
 #pragma unroll
     for (int o = D; o < 32; o <<= 1) {
@@ -362,7 +367,9 @@ __global__ void la_partial_sum_kernel(const float* __restrict__ ws, int splits, 
 }
 
 static int la_splits_allheads(int N, int S) {
-  int s = (3 * kNumSMs + N - 1) / N;
+  // la_reduce_allheads_kernel runs 3 CTAs per SM (64 KB smem, 72 registers): size the grid N x splits to fit ONE wave
+  // of 3 x 148 resident CTAs (rounding up gave 448 CTAs for N = 32: a 4-CTA second wave doubled the kernel time)
+  int s = (3 * kNumSMs) / N;
   const int maxs = ceil_div(S, 4 * LA2_T);
   if (s > maxs) s = maxs;
   if (s < 1) s = 1;

@@ -485,6 +485,39 @@ __global__ void split_groups_kernel(const float* __restrict__ x, long long sb, l
     lo[idx] = v - h;
   }
 }
+// float4 variant (K, ld, sb, sh multiples of 4 and 16-byte aligned pointers): one 16-byte load, two 16-byte stores
+__global__ void __launch_bounds__(256) split_groups_vec_kernel(const float* __restrict__ x, long long sb, long long sh,
+                                                               int ld, int H, int G, int rows, int K4,
+                                                               float4* __restrict__ hi, float4* __restrict__ lo) {
+  const long long total = (long long)G * rows * K4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k4 = (int)(idx % K4);
+    const long long t = idx / K4;
+    const int r = (int)(t % rows);
+    const int g = (int)(t / rows);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)(g / H) * sb + (size_t)(g % H) * sh +
+                                                            (size_t)r * ld) + k4);
+    float4 h;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    hi[idx] = h;
+    lo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
+static void launch_split_groups(const float* x, long long sb, long long sh, int ld, int H, int G, int rows, int K,
+                                float* hi, float* lo, cudaStream_t st) {
+  const int blocks = kNumSMs * 8;
+  const bool vec = (K % 4 == 0) && (ld % 4 == 0) && (sb % 4 == 0) && (sh % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15u) == 0;
+  if (vec)
+    split_groups_vec_kernel<<<blocks, 256, 0, st>>>(x, sb, sh, ld, H, G, rows, K / 4, reinterpret_cast<float4*>(hi),
+                                                    reinterpret_cast<float4*>(lo));
+  else
+    split_groups_kernel<<<blocks, 256, 0, st>>>(x, sb, sh, ld, H, G, rows, K, hi, lo);
+}
 
 struct SplitOps { float *ahi, *alo, *bhi, *blo; };
 
@@ -498,10 +531,9 @@ static int prepare_operands(const ScoreArgs& a, float* ws, size_t ws_bytes, Spli
   o->bhi = reinterpret_cast<float*>(base + 2 * na);
   o->blo = reinterpret_cast<float*>(base + 2 * na + nb);
   if (!split_done) {
-    const int blocks = kNumSMs * 8;
-    split_groups_kernel<<<blocks, 256, 0, st>>>(a.A, a.sAb, a.sAh, a.lda, a.H, a.G, a.L, a.K, o->ahi, o->alo);
+    launch_split_groups(a.A, a.sAb, a.sAh, a.lda, a.H, a.G, a.L, a.K, o->ahi, o->alo, st);
     FAR_CHECK_LAUNCH();
-    split_groups_kernel<<<blocks, 256, 0, st>>>(a.B, a.sBb, a.sBh, a.ldb, a.H, a.G, a.S, a.K, o->bhi, o->blo);
+    launch_split_groups(a.B, a.sBb, a.sBh, a.ldb, a.H, a.G, a.S, a.K, o->bhi, o->blo, st);
     FAR_CHECK_LAUNCH();
   }
   // dense [G][rows][K]: 4-D map dims (K, rows, H, G/H)
