@@ -7,7 +7,7 @@ import csv
 import json
 import sys
 
-CLASSES = {"tc_gemm_kernel": "tc_gemm_kernel", "tc_score_kernel": "tc_score_kernel", "tc_emm_pv_kernel": "tc_emm_pv_kernel",
+CLASSES = {"tc_gemm_kernel": "tc_gemm_kernel", "tc_score_kernel": ("tc_score_kernel", "tc_lse64_kernel"), "tc_emm_pv_kernel": "tc_emm_pv_kernel",
            "la_reduce": "la_reduce_allheads_kernel", "la_apply": "la_apply_allheads_kernel", "la_small_kernel": "la_small",
            "layernorm": "layernorm", "linear_simt_kernel": "linear_simt_kernel", "fpn_fuse": "stem_conv7x7s2",
            "fine_window_gather_kernel": "fine_window_gather_kernel", "fine_match_kernel": "fine_match_kernel"}
@@ -31,7 +31,8 @@ for i in ids:
     if not (lo <= i < hi):
         continue
     for cls, pat in CLASSES.items():
-        if pat in launch[i]["name"]:
+        pats = pat if isinstance(pat, tuple) else (pat,)
+        if any(q in launch[i]["name"] for q in pats):
             a = acc.setdefault(cls, {"bytes": 0.0, "ns": 0.0, "n": 0})
             a["bytes"] += launch[i]["bytes"]
             a["ns"] += launch[i]["ns"]
