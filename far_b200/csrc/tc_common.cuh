@@ -107,6 +107,10 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format TF32 (2) [7,10)/[10,13), K-major A and B,
 // N >> 3 in [17,23), M >> 4 in [24,29).
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// Same with N = 2*BN: one instruction computes  [main | cross] += A_hi x [B_hi ; B_lo]  (the B_hi and B_lo tiles are
+// adjacent in shared memory, the main and cross accumulators adjacent in TMEM).  With  cross += A_lo x B_hi  that is 2
+// instructions and 20 KB of operand fetch per k-step instead of 3 and 24 KB -- the shared-memory port paces these MMAs.
+constexpr uint32_t kIdescTf32N2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 
 // x = hi + lo with hi = tf32-truncated x.  Handles the [x1 | x2] concatenation: dst row stride = K1 + K2.

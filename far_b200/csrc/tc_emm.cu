@@ -195,7 +195,7 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     // Whole warp in the (warp-uniform) loop, barrier waits by all lanes, one elected lane issues (tc_common.cuh:
     // elect_one): UTCHMMA back to back instead of ~10 SASS instructions of ELECT/BRA/R2UR glue per 32-48-cycle MMA.
     {
-      constexpr uint32_t idS = idesc_tf32(BM, EBJ), idT = idesc_tf32(BM, EDVP);
+      constexpr uint32_t idS = idesc_tf32(BM, EBJ), idS2 = idesc_tf32(BM, 2 * EBJ), idT = idesc_tf32(BM, EDVP);
       mbar_wait(q_full, 0);
       tc_fence_after();
       auto issue_S = [&](int jt) {   // S(jt) = Q K(jt)^T into S/P buffer jt & 1
@@ -217,9 +217,12 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-              umma_tf32(tS_cross, dQlo + koff, dKhi + koff, idS, (kb | k) ? 1u : 0u);
-              umma_tf32(tS_cross, dQhi + koff, dKlo + koff, idS, 1u);
-              umma_tf32(tS_main, dQhi + koff, dKhi + koff, idS, (kb | k) ? 1u : 0u);
+              // [S_main | S_cross] += Qhi x [Khi ; Klo] as ONE N = 128 instruction (K hi/lo tiles adjacent in shared
+              // memory, S main/cross adjacent in TMEM): 64 + 48 cycles per k-step instead of 3 x 48 (SS MMAs are paced by
+              // the shared-memory port, profiles/r1_mma_rate_microbench.md)
+              umma_tf32(tS_main, dQhi + koff, dKhi + koff, idS2, (kb | k) ? 1u : 0u);
+              umma_tf32(tS_cross, dQlo + koff, dKhi + koff, idS, 1u);
+              (void)dKlo;
             }
           }
           umma_commit(s_full(st));

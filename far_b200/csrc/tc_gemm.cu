@@ -205,9 +205,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             for (int k = 0; k < BK / UMMA_K; ++k) {
               if (p.dbg & 4) break;
               const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128-byte swizzle row
-              umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
-              umma_tf32(tmem_small, dAhi + koff, dBlo + koff, kIdescTf32, 1u);
-              umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+              umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32N2, (kb | k) ? 1u : 0u);  // [main|cross] += Ahi [Bhi;Blo]
+              umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, 1u);                    // cross += Alo Bhi
+              (void)dBlo;
             }
             umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
             if (kb == kblocks - 1) umma_commit(tfull_bar(acc));  // accumulator complete
@@ -238,7 +238,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
             h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
             h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            a4[ct + i * 128] = h;
+            // kind::tf32 reads the top 19 bits of each fp32 operand word (the low 13 mantissa bits are ignored), so the
+            // raw tile already IS the hi operand: only lo = x - trunc(x) is written (one third less converter traffic
+            // through the shared-memory port that paces the MMAs).  FAR_TC_DBG bit 128 restores the explicit hi store.
+            if (p.dbg & 128) a4[ct + i * 128] = h;
             l4[ct + i * 128] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA reads

@@ -138,9 +138,9 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-              umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
-              umma_tf32(tmem_small, dAhi + koff, dBlo + koff, kIdescTf32, 1u);
-              umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+              umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32N2, (kb | k) ? 1u : 0u);  // [main|cross] += Ahi [Bhi;Blo]
+              umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, 1u);                    // cross += Alo Bhi
+              (void)dBlo;
             }
             umma_commit(empty_bar(stage));
             if (kb == kblocks - 1) umma_commit(tfull_bar(acc));
@@ -370,9 +370,9 @@ tc_lse64_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constan
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-            umma_tf32(t_cross, dQlo + koff, dKhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
-            umma_tf32(t_cross, dQhi + koff, dKlo + koff, kIdescTf32, 1u);
-            umma_tf32(t_main, dQhi + koff, dKhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);
+            umma_tf32(t_main, dQhi + koff, dKhi + koff, kIdescTf32N2, (kb | k) ? 1u : 0u);   // [main|cross] += Qhi [Khi;Klo]
+            umma_tf32(t_cross, dQlo + koff, dKhi + koff, kIdescTf32, 1u);                    // cross += Qlo Khi
+            (void)dKlo;
           }
         }
         umma_commit(k_empty(st));
