@@ -1,0 +1,78 @@
+"""Prediction cache: on-disk format and axis convention of the reference
+(lightning_loftr.py:348-360 writer, test_streetlearn_interiornet.py:250-267 reader), restated with numpy here."""
+import os
+
+import numpy as np
+import torch
+
+from far_b200 import pred_cache
+
+
+def _reference_reader(parent, i):
+    """The reference's reader, verbatim arithmetic (numpy float64)."""
+    pred_path = os.path.join(parent, 'test', 'loftr_preds', str(i) + '.pt')
+    num_corr_path = os.path.join(parent, 'test', 'loftr_num_correspondences', str(i) + '.pt')
+    if os.path.exists(pred_path) and os.path.exists(num_corr_path):
+        loftr_preds = torch.load(pred_path).unsqueeze(0)
+        loftr_num_corr = torch.load(num_corr_path).unsqueeze(0)
+        loftr_preds = loftr_preds.cpu().numpy()[0]
+        T = np.eye(4)
+        T[:3] = loftr_preds
+        flip_axis = np.array([[1, 0, 0, 0], [0, -1, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]])
+        T = flip_axis @ T @ np.linalg.inv(flip_axis)
+        flip_axis = np.array([[0, 1, 0, 0], [1, 0, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]])
+        T = flip_axis @ T @ np.linalg.inv(flip_axis)
+        return torch.from_numpy(T.astype(np.double)).unsqueeze(0), loftr_num_corr
+    return torch.eye(4)[:3].unsqueeze(0), torch.tensor([0])
+
+
+def _random_pose(g):
+    q, _ = np.linalg.qr(g.standard_normal((3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return q, g.standard_normal(3)
+
+
+def test_roundtrip_matches_reference_reader(tmp_path):
+    g = np.random.default_rng(3)
+    parent = str(tmp_path)
+    poses, counts = [], []
+    for i in range(5):
+        R, t = _random_pose(g)
+        n = int(g.integers(0, 1000))
+        pred_cache.save_prediction(parent, 'test', i, R, t, n)
+        poses.append(np.concatenate([R, t[:, None]], 1))
+        counts.append(n)
+    for i in range(5):
+        stored = torch.load(os.path.join(parent, 'test', 'loftr_preds', f'{i}.pt'))
+        assert stored.dtype == torch.float64 and stored.shape == (3, 4)      # the writer's format
+        assert np.array_equal(stored.numpy(), poses[i])
+        T_ref, nc_ref = _reference_reader(parent, i)
+        T, nc = pred_cache.load_prediction(parent, 'test', i)
+        assert T.dtype == torch.float64 and T.shape == (1, 4, 4)
+        assert torch.equal(T, T_ref) and torch.equal(nc, nc_ref) and int(nc) == counts[i]
+    # missing pair: identity [1,3,4] and zero correspondences, like the reference
+    T, nc = pred_cache.load_prediction(parent, 'test', 99)
+    T_ref, nc_ref = _reference_reader(parent, 99)
+    assert torch.equal(T, T_ref) and torch.equal(nc, nc_ref)
+
+
+def test_batch_and_in_memory_paths(tmp_path):
+    g = np.random.default_rng(4)
+    parent = str(tmp_path)
+    poses = torch.from_numpy(np.stack([np.concatenate([R, t[:, None]], 1) for R, t in (_random_pose(g) for _ in range(4))]))
+    counts = torch.tensor([10, 0, 500, 999])
+    pred_cache.save_batch(parent, 'test', [0, 1, 2, 3], poses.float(), counts)   # float32 in, float64 on disk
+    T, nc = pred_cache.load_batch(parent, 'test', [0, 1, 2, 3, 7])
+    assert T.shape == (5, 4, 4) and T.dtype == torch.float64 and nc.tolist() == [10, 0, 500, 999, 0]
+    assert torch.equal(T[4], torch.eye(4, dtype=torch.float64))
+    # in-memory path == disk path (up to the float32 the poses were saved from)
+    T_mem = pred_cache.to_vit_convention(poses.float())
+    assert torch.allclose(T_mem, T[:4], atol=0, rtol=0)
+    # conjugation by axis flips keeps a rigid transform rigid and maps t -> (t_y, -t_x ... ) permutation/sign only
+    Rm = T_mem[:, :3, :3]
+    assert torch.allclose(Rm @ Rm.transpose(1, 2), torch.eye(3, dtype=torch.float64).expand(4, 3, 3), atol=1e-6)
+    assert torch.allclose(torch.linalg.det(Rm), torch.ones(4, dtype=torch.float64), atol=1e-6)
+    out = {'loftr_rt': poses.float(), 'num_matches': counts}
+    lp, n = pred_cache.from_pipeline(out)
+    assert torch.equal(lp, T_mem) and n.dtype == torch.int64
