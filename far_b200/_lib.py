@@ -62,6 +62,10 @@ _SIGS = {
     "far_eight_point": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, c_size_t, _P]),
     "far_essential_decompose": (c_int, [_P, c_int, _P, _P, _P, _P]),
     "far_pose_from_matches": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "far_prior_ransac_score": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, c_int, c_float, c_float, _P, _P, _P,
+                                       _P, _P, _P]),
+    "far_pose_from_essential_workspace_bytes": (c_size_t, [c_int]),
+    "far_pose_from_essential": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "far_emm_bilinear_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "far_emm_bilinear_attn": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, c_int, _P,
                                       c_size_t, _P]),

@@ -349,7 +349,8 @@ __global__ void __launch_bounds__(64) pose_solve_kernel(const double* __restrict
 // motion_from_essential (essential.py:60-62) -- the first candidate with the most votes wins (metrics.py:165-170
 // keeps the first strictly-better recoverPose result).
 __global__ void __launch_bounds__(128) pose_select_kernel(RaggedPts pts, int P, const float* __restrict__ cand,
-                                                          float* __restrict__ Rt, int* __restrict__ npos) {
+                                                          float* __restrict__ Rt, int* __restrict__ npos,
+                                                          const unsigned char* __restrict__ mask = nullptr) {
   const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (pair >= P) return;
   const int n = pts.count(pair);
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(128) pose_select_kernel(RaggedPts pts, int P, 
   int votes[4] = {0, 0, 0, 0};
   if (n >= 8) {
     for (int i = lane; i < n; i += 32) {
+      if (mask != nullptr && !mask[(size_t)pts.off[pair] + i]) continue;   // RANSAC round: inliers of the best model only
       float x0, y0, x1, y1, w;
       pts.load(pair, i, x0, y0, x1, y1, w);
 #pragma unroll
@@ -390,6 +392,145 @@ __global__ void __launch_bounds__(128) pose_select_kernel(RaggedPts pts, int P, 
     }
     npos[pair] = (n >= 8) ? best : 0;
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Prior-guided RANSAC, scoring step (mp3d_loftr/third_party/prior_ransac/ransac.py:203-231 `get_prior_estimate`,
+// :256-292 `verify`, :303-308 `remove_bad_models`): one warp per (pair, hypothesis).
+//   prior score = -(min_k mean |[R_k | T] p - prior_rt p|)^2 / lambda   over a fixed point cloud, (R_1, R_2, T) from
+//                 decompose_essential_matrix(E)  (use_noexp_prior_scoring, :401-404)
+//   inlier count = #{ i : sampson(E, x0_i, x1_i) <= inl_th }            (squared Sampson distance, K-normalised points)
+// score[p,h] = count + prior, or -inf for a degenerate model (min |diag E| <= 1e-4).
+__device__ __forceinline__ float sampson_sq(const float (&E)[9], float x0, float y0, float x1, float y1) {
+  // l = E x0h (epipolar line in image 1), m = E^T x1h
+  const float lx = E[0] * x0 + E[1] * y0 + E[2], ly = E[3] * x0 + E[4] * y0 + E[5], lz = E[6] * x0 + E[7] * y0 + E[8];
+  const float mx = E[0] * x1 + E[3] * y1 + E[6], my = E[1] * x1 + E[4] * y1 + E[7];
+  const float num = x1 * lx + y1 * ly + lz;
+  return num * num / (lx * lx + ly * ly + mx * mx + my * my);
+}
+
+__global__ void __launch_bounds__(256) ransac_score_kernel(RaggedPts pts, int P, int H, const float* __restrict__ models,
+                                                           const float* __restrict__ prior_rt,
+                                                           const float* __restrict__ pcl, int npcl, float prior_lambda,
+                                                           float inl_th, float* __restrict__ scores) {
+  const int h = blockIdx.x * 8 + (threadIdx.x >> 5), pair = blockIdx.y, lane = threadIdx.x & 31;
+  if (h >= H) return;
+  const int n = pts.count(pair);
+  float E[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) E[k] = models[((size_t)pair * H + h) * 9 + k];
+  float* out = scores + (size_t)pair * H + h;
+  if (n < 8 || !(fminf(fminf(fabsf(E[0]), fabsf(E[4])), fabsf(E[8])) > 1e-4f)) {
+    if (lane == 0) *out = -INFINITY;
+    return;
+  }
+  float prior = 0.f;
+  if (prior_rt != nullptr) {
+    float r1[9], r2[9], tt[3];
+    essential_decompose(E, r1, r2, tt);
+    const float* pr = prior_rt + (size_t)pair * 12;
+    const float tn = rsqrtf(pr[3] * pr[3] + pr[7] * pr[7] + pr[11] * pr[11]);   // setup_prior: unit translation (:180)
+    float e1 = 0.f, e2 = 0.f;
+    for (int j = lane; j < npcl; j += 32) {
+      const float px = pcl[j * 3], py = pcl[j * 3 + 1], pz = pcl[j * 3 + 2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float tg = pr[k * 4] * px + pr[k * 4 + 1] * py + pr[k * 4 + 2] * pz + pr[k * 4 + 3] * tn;
+        e1 += fabsf(r1[k * 3] * px + r1[k * 3 + 1] * py + r1[k * 3 + 2] * pz + tt[k] - tg);
+        e2 += fabsf(r2[k * 3] * px + r2[k * 3 + 1] * py + r2[k * 3 + 2] * pz + tt[k] - tg);
+      }
+    }
+    e1 = warp_sum(e1);
+    e2 = warp_sum(e2);
+    const float e = fminf(e1, e2) / (3.f * (float)npcl);
+    prior = -e * e / prior_lambda;
+  }
+  int cnt = 0;
+  for (int i = lane; i < n; i += 32) {
+    float x0, y0, x1, y1, w;
+    pts.load(pair, i, x0, y0, x1, y1, w);
+    cnt += sampson_sq(E, x0, y0, x1, y1) <= inl_th ? 1 : 0;
+  }
+  cnt = warp_sum(cnt);
+  if (lane == 0) *out = (float)cnt + prior;
+}
+
+// argmax over the hypotheses of a pair (lowest index among equal scores, like torch.argmax on CPU), then the inlier
+// masks / counts of the winner at inl_th, inl_th/10, inl_th/100 (:279-283).  One CTA per pair.
+__global__ void __launch_bounds__(256) ransac_select_kernel(RaggedPts pts, int P, int H, const float* __restrict__ models,
+                                                            const float* __restrict__ scores, float inl_th,
+                                                            int* __restrict__ best_idx, float* __restrict__ best_E,
+                                                            int* __restrict__ counts3, unsigned char* __restrict__ mask) {
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  __shared__ int sc[3];
+  const int pair = blockIdx.x, t = threadIdx.x;
+  const int n = pts.count(pair);
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int h = t; h < H; h += 256) {
+    const float v = scores[(size_t)pair * H + h];
+    if (v > bv) { bv = v; bi = h; }   // ascending h per thread: keeps the lowest index
+  }
+  sv[t] = bv; si[t] = bi;
+  if (t < 3) sc[t] = 0;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) {
+      const float v = sv[t + o];
+      const int i = si[t + o];
+      if (v > sv[t] || (v == sv[t] && i < si[t])) { sv[t] = v; si[t] = i; }
+    }
+    __syncthreads();
+  }
+  const bool ok = sv[0] > -INFINITY && n >= 8;
+  const int best = ok ? si[0] : -1;
+  float E[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) E[k] = ok ? models[((size_t)pair * H + best) * 9 + k] : 0.f;
+  int c0 = 0, c1 = 0, c2 = 0;
+  for (int i = t; i < n; i += 256) {
+    unsigned char m = 0;
+    if (ok) {
+      float x0, y0, x1, y1, w;
+      pts.load(pair, i, x0, y0, x1, y1, w);
+      const float e = sampson_sq(E, x0, y0, x1, y1);
+      m = e <= inl_th ? 1 : 0;
+      c0 += m;
+      c1 += e <= inl_th / 10.0f ? 1 : 0;
+      c2 += e <= inl_th / 100.0f ? 1 : 0;
+    }
+    mask[(size_t)pts.off[pair] + i] = m;
+  }
+  c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
+  if ((t & 31) == 0) { atomicAdd(&sc[0], c0); atomicAdd(&sc[1], c1); atomicAdd(&sc[2], c2); }
+  __syncthreads();
+  if (t == 0) {
+    best_idx[pair] = best;
+    counts3[pair * 3 + 0] = sc[0]; counts3[pair * 3 + 1] = sc[1]; counts3[pair * 3 + 2] = sc[2];
+  }
+  if (t < 9) best_E[(size_t)pair * 9 + t] = E[t];
+}
+
+// E -> the 4 motion candidates in the cand[21] layout of pose_select_kernel; E == 0 (no valid model) -> identity.
+__global__ void __launch_bounds__(64) essential_to_cand_kernel(const float* __restrict__ E, int P, float* __restrict__ cand) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= P) return;
+  float e[9], r1[9], r2[9], tt[3];
+  float nrm = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { e[k] = E[(size_t)pair * 9 + k]; nrm += e[k] * e[k]; }
+  if (nrm > 0.f) {
+    essential_decompose(e, r1, r2, tt);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { r1[k] = (k % 4 == 0) ? 1.f : 0.f; r2[k] = r1[k]; }
+    tt[0] = tt[1] = tt[2] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { cand[(size_t)pair * 21 + k] = r1[k]; cand[(size_t)pair * 21 + 9 + k] = r2[k]; }
+  cand[(size_t)pair * 21 + 18] = tt[0]; cand[(size_t)pair * 21 + 19] = tt[1]; cand[(size_t)pair * 21 + 20] = tt[2];
 }
 
 }  // namespace far
@@ -436,6 +577,47 @@ extern "C" int far_pose_from_matches(const float* mkpts0, const float* mkpts1, c
   pose_solve_kernel<<<ceil_div(N, 64), 64, 0, st>>>(rec, N, E, cand);
   FAR_CHECK_LAUNCH();
   pose_select_kernel<<<ceil_div(N, 4), 128, 0, st>>>(pts, N, cand, Rt, n_pos);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+// ---- prior-guided RANSAC round: scoring of H hypotheses per pair + pose of the winner ----------
+extern "C" int far_prior_ransac_score(const float* mkpts0, const float* mkpts1, const long long* offsets, int P,
+                                      const float* K0, const float* K1, const float* models, int H,
+                                      const float* prior_rt, const float* pcl, int npcl, float prior_lambda,
+                                      float inl_th, float* scores, int* best_idx, float* best_E, int* counts3,
+                                      unsigned char* inlier_mask, void* stream) {
+  if (P <= 0 || H <= 0) return FAR_OK;
+  FAR_REQUIRE(mkpts0 && mkpts1 && offsets && K0 && K1 && models && scores && best_idx && best_E && counts3 &&
+              inlier_mask && (prior_rt == nullptr || (pcl != nullptr && npcl > 0 && prior_lambda > 0.f)));
+  cudaStream_t st = (cudaStream_t)stream;
+  RaggedPts pts{mkpts0, mkpts1, nullptr, offsets, K0, K1};
+  {
+    ProfScope prof(PROF_SOLVER, 0.0, 0.0, st);
+    ransac_score_kernel<<<dim3(ceil_div(H, 8), P), 256, 0, st>>>(pts, P, H, models, prior_rt, pcl, npcl, prior_lambda,
+                                                                 inl_th, scores);
+  }
+  FAR_CHECK_LAUNCH();
+  ransac_select_kernel<<<P, 256, 0, st>>>(pts, P, H, models, scores, inl_th, best_idx, best_E, counts3, inlier_mask);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+extern "C" size_t far_pose_from_essential_workspace_bytes(int P) { return (size_t)P * 21 * 4 + 256; }
+
+// (R | t) of an essential matrix by the cheirality vote of pose_from_matches, restricted to `mask` (NULL: all matches).
+extern "C" int far_pose_from_essential(const float* mkpts0, const float* mkpts1, const unsigned char* mask,
+                                       const long long* offsets, int P, const float* K0, const float* K1,
+                                       const float* E, float* Rt, int* n_pos, float* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  if (P <= 0) return FAR_OK;
+  FAR_REQUIRE(mkpts0 && mkpts1 && offsets && K0 && K1 && E && Rt && n_pos && workspace);
+  if (workspace_bytes < (size_t)P * 21 * 4) return FAR_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  RaggedPts pts{mkpts0, mkpts1, nullptr, offsets, K0, K1};
+  essential_to_cand_kernel<<<ceil_div(P, 64), 64, 0, st>>>(E, P, workspace);
+  FAR_CHECK_LAUNCH();
+  pose_select_kernel<<<ceil_div(P, 4), 128, 0, st>>>(pts, P, workspace, Rt, n_pos, mask);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }

@@ -336,6 +336,45 @@ def pose_from_matches(mkpts0, mkpts1, mconf, offsets, K0, K1):
     return E, Rt, npos
 
 
+def prior_ransac_score(mkpts0, mkpts1, offsets, K0, K1, models, prior_rt, pcl, prior_lambda, inl_th):
+    """RANSAC.get_prior_estimate + verify + remove_bad_models (third_party/prior_ransac/ransac.py:203-231,256-292,
+    303-308) for every pair of a ragged batch.  models [P,H,3,3]; prior_rt [P,3,4] or None; pcl [npcl,3].
+    Returns scores [P,H], best_idx [P] int32, best_E [P,3,3], counts3 [P,3] int32, inlier_mask [M] uint8."""
+    lib = L.load()
+    P, H = models.shape[0], models.shape[1]
+    dev = models.device
+    M = int(mkpts0.shape[0])
+    scores = torch.empty((P, H), dtype=torch.float32, device=dev)
+    best = torch.empty(P, dtype=torch.int32, device=dev)
+    bestE = torch.empty((P, 3, 3), dtype=torch.float32, device=dev)
+    counts3 = torch.empty((P, 3), dtype=torch.int32, device=dev)
+    mask = torch.zeros(max(M, 1), dtype=torch.uint8, device=dev)
+    pr = f32c(prior_rt) if prior_rt is not None else None
+    pc = f32c(pcl) if pcl is not None else None
+    with _timed("far_prior_ransac_score"):
+        check(lib.far_prior_ransac_score(ptr(f32c(mkpts0)), ptr(f32c(mkpts1)), ptr(offsets), P, ptr(f32c(K0)),
+                                         ptr(f32c(K1)), ptr(f32c(models)), H, ptr(pr), ptr(pc),
+                                         pc.shape[0] if pc is not None else 0, float(prior_lambda), float(inl_th),
+                                         ptr(scores), ptr(best), ptr(bestE), ptr(counts3), ptr(mask), stream()),
+              "far_prior_ransac_score")
+    return scores, best, bestE, counts3, mask[:M]
+
+
+def pose_from_essential(mkpts0, mkpts1, mask, offsets, K0, K1, E):
+    """cv2.recoverPose-style candidate selection (metrics.py:164-170) for given essential matrices E [P,3,3], voting over
+    the matches with mask != 0.  Returns Rt [P,3,4], n_pos [P] int32."""
+    lib = L.load()
+    P = E.shape[0]
+    dev = E.device
+    Rt = torch.empty((P, 3, 4), dtype=torch.float32, device=dev)
+    npos = torch.empty(P, dtype=torch.int32, device=dev)
+    ws = _ws(lib.far_pose_from_essential_workspace_bytes(P), dev)
+    check(lib.far_pose_from_essential(ptr(f32c(mkpts0)), ptr(f32c(mkpts1)), ptr(mask) if mask is not None else None,
+                                      ptr(offsets), P, ptr(f32c(K0)), ptr(f32c(K1)), ptr(f32c(E)), ptr(Rt), ptr(npos),
+                                      ptr(ws), ws.numel(), stream()), "far_pose_from_essential")
+    return Rt, npos
+
+
 def emm_bilinear_attn(qkv1, qkv2, pos, num_heads, scale, engine=L.ENGINE_AUTO):
     """CrossAttention core (transformer.py:275-292): qkv1,qkv2 [B,N,3*C] (output of the shared qkv Linear),
     pos [1 or B, N, 6] -> fundamental_1, fundamental_2 [B,h,d+6,d+6]."""

@@ -16,10 +16,15 @@ from .loftr.pose import pose_mean_6d, pose_std_6d, rotation_6d_to_matrix
 
 
 class FarPosePipeline:
-    def __init__(self, model, K0, K1, fine_pred_steps=None):
+    def __init__(self, model, K0, K1, fine_pred_steps=None, prior_ransac=False, ransac_kwargs=None):
         self.model = model
         self.K0, self.K1 = K0, K1
         self.steps = fine_pred_steps if fine_pred_steps is not None else model.config.get('fine_pred_steps', 1)
+        # prior_ransac=True: the solver call between the two head invocations is the prior-guided RANSAC round of the
+        # recipe of record (lightning_loftr.py:343-344, metrics.py:100-123) run on the GPU (far_b200/ransac.py) with the
+        # first head prediction as the prior, instead of a plain re-run of the weighted 8-point solver.
+        self.prior_ransac = prior_ransac
+        self.ransac_kwargs = ransac_kwargs or {}
 
     @torch.no_grad()
     def __call__(self, image0, image1):
@@ -36,7 +41,15 @@ class FarPosePipeline:
             for i in range(self.steps):
                 m.forward_rt_prediction(data)
                 if i == 0 and self.steps > 1:
-                    estimate_pose_batched(data, K0, K1)
+                    if self.prior_ransac:
+                        from .ransac import prior_ransac_round
+                        rr0 = data['regressed_rt']
+                        d0 = rr0.device
+                        R0 = rotation_6d_to_matrix(rr0[:, 3:] * pose_std_6d[3:].to(d0) + pose_mean_6d[3:].to(d0))
+                        t0 = rr0[:, :3] * pose_std_6d[:3].to(d0) + pose_mean_6d[:3].to(d0)
+                        prior_ransac_round(data, K0, K1, torch.cat([R0, t0.unsqueeze(-1)], dim=-1), **self.ransac_kwargs)
+                    else:
+                        estimate_pose_batched(data, K0, K1)
             rr = data['regressed_rt']
             dev = rr.device
             R = rotation_6d_to_matrix(rr[:, 3:] * pose_std_6d[3:].to(dev) + pose_mean_6d[3:].to(dev))

@@ -183,6 +183,27 @@ int far_pose_from_matches(const float* mkpts0, const float* mkpts1, const float*
                           float* Rt, int* n_pos, float* workspace /* far_eight_point_workspace_bytes(N) */,
                           size_t workspace_bytes, void* stream);
 
+/* ---- prior-guided RANSAC round, scoring step --------------------------------------------
+ * For every pair p (ragged matches [offsets[p], offsets[p+1]) of pixel keypoints, K-normalised on the fly as
+ * mp3d_loftr/src/utils/metrics.py:88-89) and every hypothesis h of models [P,H,3,3]:
+ *   scores[p,h] = #{ i : sampson_sq(E, x0_i, x1_i) <= inl_th } + prior(E)          (ransac.py:256-275 `verify`)
+ *   prior(E)    = -(min_k mean |[R_k | T] pcl - prior_rt[p] pcl|)^2 / prior_lambda  (ransac.py:203-231, :401-404;
+ *                 (R_1, R_2, T) = decompose_essential_matrix(E); prior_rt translation normalised as in :180;
+ *                 prior_rt == NULL: no prior term)
+ *   -inf for degenerate models (min |diag E| <= 1e-4, ransac.py:303-308) and for pairs with < 8 matches.
+ * Then per pair: best_idx = argmax_h (lowest index on ties; -1 if none), best_E [P,3,3], counts3 [P,3] = inliers of the
+ * winner at inl_th, inl_th/10, inl_th/100 (:279-283), inlier_mask [M] (uint8) at inl_th. */
+int far_prior_ransac_score(const float* mkpts0, const float* mkpts1, const long long* offsets, int P, const float* K0,
+                           const float* K1, const float* models, int H, const float* prior_rt, const float* pcl,
+                           int npcl, float prior_lambda, float inl_th, float* scores, int* best_idx, float* best_E,
+                           int* counts3, unsigned char* inlier_mask, void* stream);
+/* (R | t) [P,3,4] of essential matrices E [P,3,3] by the cheirality vote of far_pose_from_matches (the criterion of
+ * cv2.recoverPose, metrics.py:164-170) over the matches with mask != 0 (mask NULL: all); E == 0 -> identity pose. */
+size_t far_pose_from_essential_workspace_bytes(int P);
+int far_pose_from_essential(const float* mkpts0, const float* mkpts1, const unsigned char* mask,
+                            const long long* offsets, int P, const float* K0, const float* K1, const float* E,
+                            float* Rt, int* n_pos, float* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- CrossAttention.forward core (mp3d: transformer.py:266-303; 8pt-ViT: vision_transformer.py:177-208)
  * qkv1,qkv2: [B,Ntok,3,h,d] (the output of the shared qkv Linear on the two images), pos: [Bpos,Ntok,6]
  * (Bpos = 1 broadcasts).  Computes, per (b,head), for X in {1,2}:

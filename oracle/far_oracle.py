@@ -651,6 +651,74 @@ def cheirality_count(R, t, x0, x1):
 
 
 # --------------------------------------------------------------------------------------- deterministic synthetic inputs
+# --------------------------------------------------------------------------------------- 8f rank 2: prior-guided RANSAC
+def sampson_epipolar_distance(pts1, pts2, Fm):
+    """kornia 0.7.1 `sampson_epipolar_distance(..., squared=True)` (un-vendored; restated from its public definition,
+    used at ransac.py:151,256-268):  (p2^T F p1)^2 / (|(F p1)_{1:2}|^2 + |(F^T p2)_{1:2}|^2).  pts [*,N,2], Fm [*,3,3]."""
+    p1 = F.pad(pts1, [0, 1], value=1.0)
+    p2 = F.pad(pts2, [0, 1], value=1.0)
+    l1in2 = p1 @ Fm.transpose(-2, -1)
+    l2in1 = p2 @ Fm
+    num = (p2 * l1in2).sum(-1).pow(2)
+    den = l1in2[..., :2].norm(2, dim=-1).pow(2) + l2in1[..., :2].norm(2, dim=-1).pow(2)
+    return num / den
+
+
+def symmetrical_epipolar_distance(pts1, pts2, Fm):
+    """kornia 0.7.1 `symmetrical_epipolar_distance(..., squared=True)` (ransac.py:364)."""
+    p1 = F.pad(pts1, [0, 1], value=1.0)
+    p2 = F.pad(pts2, [0, 1], value=1.0)
+    l1in2 = p1 @ Fm.transpose(-2, -1)
+    l2in1 = p2 @ Fm
+    num = (p2 * l1in2).sum(-1).pow(2)
+    return num * (1.0 / l1in2[..., :2].norm(2, dim=-1).pow(2) + 1.0 / l2in1[..., :2].norm(2, dim=-1).pow(2))
+
+
+def essential_from_prior_rt(RT):
+    """ransac.py:63-71 `fundamental_from_RT` (which returns E, not F): kornia `essential_from_Rt(I, 0, R, t)` = [t]_x R."""
+    R, t = RT[..., :3, :3], RT[..., :3, 3]
+    z = torch.zeros_like(t[..., 0])
+    tx = torch.stack([torch.stack([z, -t[..., 2], t[..., 1]], -1), torch.stack([t[..., 2], z, -t[..., 0]], -1),
+                      torch.stack([-t[..., 1], t[..., 0], z], -1)], -2)
+    return tx @ R
+
+
+def ransac_bias_weight(kp1, kp2, prior_rt, sigma_sq=0.1):
+    """ransac.py:358-367 with use_linear_bias_sampling: exp(-sym_epipolar(kp1, kp2, E_prior) / sigma^2).  prior_rt [3,4]
+    with unit-norm translation (setup_prior, ransac.py:180)."""
+    return torch.exp(-symmetrical_epipolar_distance(kp1[None], kp2[None], essential_from_prior_rt(prior_rt)[None]) / sigma_sq)[0]
+
+
+def ransac_prior_estimate(models, prior_rt, pcl, prior_lambda=0.3):
+    """ransac.py:203-231 + :401-404 (use_noexp_prior_scoring): each model E -> (R1, R2, T) by
+    decompose_essential_matrix; error_k = mean |[R_k | T] pcl - prior_rt pcl| over the 3 x npcl coordinates;
+    prior score = -(min(error_1, error_2))^2 / lambda.  models [H,3,3], prior_rt [3,4], pcl [npcl,3]."""
+    R1, R2, T = decompose_essential_matrix(models)
+    target = prior_rt[:, :3] @ pcl.t() + prior_rt[:, 3:]                         # [3, npcl]
+    def err(R):
+        return ((R @ pcl.t()[None] + T) - target[None]).abs().reshape(models.shape[0], -1).mean(1)
+    e = torch.minimum(err(R1), err(R2))
+    return -e ** 2 / prior_lambda
+
+
+def ransac_good_models(models):
+    """ransac.py:303-308 `remove_bad_models`: keep models whose main diagonal has min |.| > 1e-4."""
+    return torch.diagonal(models, dim1=1, dim2=2).abs().min(dim=1)[0] > 1e-4
+
+
+def ransac_verify(kp1, kp2, models, inl_th, prior_score):
+    """ransac.py:256-292: Sampson errors of every model on every correspondence, inlier count at inl_th plus the prior
+    score, argmax; inlier masks of the best model at inl_th, inl_th/10, inl_th/100.
+    kp [N,2], models [H,3,3], prior_score [H] -> (best index, score [H], masks [3,N])."""
+    H = models.shape[0]
+    errors = sampson_epipolar_distance(kp1[None].expand(H, -1, 2), kp2[None].expand(H, -1, 2), models)
+    inl = errors <= inl_th
+    score = inl.to(kp1).sum(dim=1) + prior_score.to(kp1)
+    best = int(score.argmax())
+    masks = torch.stack([inl[best], errors[best] <= inl_th / 10.0, errors[best] <= inl_th / 100.0])
+    return best, score, masks
+
+
 def rng(seed):
     return np.random.default_rng(seed)
 
