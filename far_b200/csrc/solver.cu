@@ -431,19 +431,23 @@ __global__ void __launch_bounds__(256) ransac_score_kernel(RaggedPts pts, int P,
     essential_decompose(E, r1, r2, tt);
     const float* pr = prior_rt + (size_t)pair * 12;
     const float tn = rsqrtf(pr[3] * pr[3] + pr[7] * pr[7] + pr[11] * pr[11]);   // setup_prior: unit translation (:180)
-    float e1 = 0.f, e2 = 0.f;
+    // The sign of T = U[:, 2] is an artefact of the SVD routine (E fixes t only up to sign).  The reference scores
+    // whichever sign LAPACK returns (ransac.py:215-224); here both signs are scored and the better one counts, which
+    // equals the reference's value whenever LAPACK's sign is the better one and is never worse.
+    float e1p = 0.f, e2p = 0.f, e1m = 0.f, e2m = 0.f;
     for (int j = lane; j < npcl; j += 32) {
       const float px = pcl[j * 3], py = pcl[j * 3 + 1], pz = pcl[j * 3 + 2];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const float tg = pr[k * 4] * px + pr[k * 4 + 1] * py + pr[k * 4 + 2] * pz + pr[k * 4 + 3] * tn;
-        e1 += fabsf(r1[k * 3] * px + r1[k * 3 + 1] * py + r1[k * 3 + 2] * pz + tt[k] - tg);
-        e2 += fabsf(r2[k * 3] * px + r2[k * 3 + 1] * py + r2[k * 3 + 2] * pz + tt[k] - tg);
+        const float a1 = r1[k * 3] * px + r1[k * 3 + 1] * py + r1[k * 3 + 2] * pz - tg;
+        const float a2 = r2[k * 3] * px + r2[k * 3 + 1] * py + r2[k * 3 + 2] * pz - tg;
+        e1p += fabsf(a1 + tt[k]); e1m += fabsf(a1 - tt[k]);
+        e2p += fabsf(a2 + tt[k]); e2m += fabsf(a2 - tt[k]);
       }
     }
-    e1 = warp_sum(e1);
-    e2 = warp_sum(e2);
-    const float e = fminf(e1, e2) / (3.f * (float)npcl);
+    e1p = warp_sum(e1p); e2p = warp_sum(e2p); e1m = warp_sum(e1m); e2m = warp_sum(e2m);
+    const float e = fminf(fminf(e1p, e2p), fminf(e1m, e2m)) / (3.f * (float)npcl);
     prior = -e * e / prior_lambda;
   }
   int cnt = 0;

@@ -689,15 +689,19 @@ def ransac_bias_weight(kp1, kp2, prior_rt, sigma_sq=0.1):
     return torch.exp(-symmetrical_epipolar_distance(kp1[None], kp2[None], essential_from_prior_rt(prior_rt)[None]) / sigma_sq)[0]
 
 
-def ransac_prior_estimate(models, prior_rt, pcl, prior_lambda=0.3):
+def ransac_prior_estimate(models, prior_rt, pcl, prior_lambda=0.3, both_signs=False):
     """ransac.py:203-231 + :401-404 (use_noexp_prior_scoring): each model E -> (R1, R2, T) by
     decompose_essential_matrix; error_k = mean |[R_k | T] pcl - prior_rt pcl| over the 3 x npcl coordinates;
-    prior score = -(min(error_1, error_2))^2 / lambda.  models [H,3,3], prior_rt [3,4], pcl [npcl,3]."""
+    prior score = -(min(error_1, error_2))^2 / lambda.  models [H,3,3], prior_rt [3,4], pcl [npcl,3].
+    both_signs=True additionally scores -T (the sign of T = U[:,2] is whatever the SVD routine returns; the CUDA
+    kernel scores both and keeps the better)."""
     R1, R2, T = decompose_essential_matrix(models)
     target = prior_rt[:, :3] @ pcl.t() + prior_rt[:, 3:]                         # [3, npcl]
-    def err(R):
-        return ((R @ pcl.t()[None] + T) - target[None]).abs().reshape(models.shape[0], -1).mean(1)
-    e = torch.minimum(err(R1), err(R2))
+    def err(R, Tt):
+        return ((R @ pcl.t()[None] + Tt) - target[None]).abs().reshape(models.shape[0], -1).mean(1)
+    e = torch.minimum(err(R1, T), err(R2, T))
+    if both_signs:
+        e = torch.minimum(e, torch.minimum(err(R1, -T), err(R2, -T)))
     return -e ** 2 / prior_lambda
 
 
