@@ -10,7 +10,8 @@
 A "step" = one pass of the whole path over one batch of synthetic pairs:
   workload `mp3d_loftr_far` (BASELINE.json configs[1]): FAR-LoFTR forward (ResNet-FPN backbone -> 3x(self,cross)
   linear-attention layers -> dual-softmax coarse matching -> 5x5 fine level) -> weighted 8-point + cheirality
-  -> FAR head x2 (regress LoFTR layers -> EMM dual-softmax bilinear attention -> gated pose MLP), batch 32 pairs,
+  -> FAR head (regress LoFTR layers -> EMM dual-softmax bilinear attention -> gated pose MLP) -> prior-guided RANSAC
+  round (2048 hypotheses / pair, the head's pose as prior) -> FAR head again (gate + blend), batch 32 pairs,
   random-init (seeded) weights, thr = 0 so random features still produce ~1.1k matches/pair.
 Prints ONE JSON line (rank 0).
 """
@@ -160,7 +161,7 @@ def run_far(args, rank, world, local_rank):
     img0_h, img1_h = build_inputs(pairs, 20240002 + rank)
     img0_h, img1_h = img0_h.pin_memory(), img1_h.pin_memory()
     K = synth.mp3d_intrinsics(pairs).to(dev)
-    pipe = FarPosePipeline(model, K, K)
+    pipe = FarPosePipeline(model, K, K, prior_ransac=not args.no_prior_ransac)
     lib = _lib.load()
 
     def barrier():
@@ -268,6 +269,8 @@ def run_far(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "mp3d_loftr_far", "pairs_per_gpu": pairs, "global_pairs": pairs * world,
                        "image": "640x480 gray", "thr": 0.0, "coarse_layers": 3, "fine_pred_steps": 2,
+                       "second_solver_call": "prior-guided RANSAC round on the GPU (2048 hypotheses/pair)"
+                       if not args.no_prior_ransac else "weighted 8-point + cheirality (as the first call)",
                        "head_trunk": "evaluated once per forward and reused by the 2nd head invocation (identical "
                                      "outputs; --no-trunk-reuse re-evaluates it)" if not args.no_trunk_reuse else
                                      "re-evaluated by each of the 2 head invocations",
@@ -302,6 +305,9 @@ def main():
     ap.add_argument("--impl", default="far", choices=["far", "reference"])
     ap.add_argument("--pairs", type=int, default=32, help="pairs per GPU per step (BASELINE configs[1]: 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prior-ransac", action="store_true",
+                    help="re-run the weighted 8-point between the two head invocations instead of the batched GPU "
+                         "prior-guided RANSAC round of the FAR recipe (far_b200/ransac.py, 2048 hypotheses per pair)")
     ap.add_argument("--no-trunk-reuse", action="store_true",
                     help="re-evaluate the FAR head trunk in both head invocations, literally as the reference does")
     args = ap.parse_args()

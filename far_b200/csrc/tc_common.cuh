@@ -13,10 +13,7 @@ constexpr int UMMA_K = 8;                   // tf32: 32 bytes of K per MMA
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;     // 16 KiB per operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES; // Ahi, Alo, Bhi, Blo
-constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 4 * BN;           // two accumulator buffers x (main hi*hi | small cross terms) = 512 columns
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ +
-                              4 * 32 * 33 * 4 /*epilogue transpose staging, one 32x33 tile per warp*/;
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -19,7 +19,7 @@ constexpr int S_STAGES = 2;                 // 2 x 64 KiB operand ring leaves ro
 constexpr int S_THREADS = 64 + 256;         // producer warp, MMA warp, 8 epilogue warps
 constexpr int SPITCH = BN + 1;              // 129: conflict-free row writes and column reads
 constexpr size_t SCORE_SMEM = 1024 + (size_t)S_STAGES * STAGE_BYTES + 256 + (size_t)BM * SPITCH * 4 + BN * 4;
-constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+constexpr float kLog2e = 1.4426950408889634f;
 
 struct ScoreTcArgs {
   int G, H, L, S, K;       // groups (= nb * H), heads per batch, rows of A, rows of B, contraction
