@@ -76,3 +76,18 @@ def test_batch_and_in_memory_paths(tmp_path):
     out = {'loftr_rt': poses.float(), 'num_matches': counts}
     lp, n = pred_cache.from_pipeline(out)
     assert torch.equal(lp, T_mem) and n.dtype == torch.int64
+
+
+def test_ransac_host_glue_vs_reference_golden(golden_dir):
+    """The torch glue of far_b200/ransac.py that needs no GPU: prior normalisation (setup_prior, ransac.py:176-186) and
+    the sampling bias weights (ransac.py:358-367) against the fixture produced by the unmodified reference."""
+    from far_b200.ransac import bias_weights, normalise_prior
+    g = np.load(os.path.join(golden_dir, "ransac.npz"))
+    kp1, kp2 = torch.from_numpy(g["kp1"]), torch.from_numpy(g["kp2"])
+    prior = torch.from_numpy(g["prior_rt"])[None].clone()
+    prior[:, :, 3] *= 3.7                                   # un-normalised on purpose
+    pn = normalise_prior(prior)
+    assert torch.allclose(pn[0, :, 3].norm(), torch.tensor(1.0), atol=1e-6)
+    assert torch.allclose(pn[0], torch.from_numpy(g["prior_rt"]), atol=1e-6)
+    bw = bias_weights(kp1, kp2, torch.zeros(kp1.shape[0], dtype=torch.int64), pn, 0.1)
+    assert (bw - torch.from_numpy(g["bias_ref"])).abs().max() < 1e-5
