@@ -723,6 +723,28 @@ def ransac_verify(kp1, kp2, models, inl_th, prior_score):
     return best, score, masks
 
 
+# --------------------------------------------------------------------------------------- 8f rank 3: map-free aggregator
+def mapfree_correlation_aggregator(vol0, vol1):
+    """mapfree_6dreg/lib/models/regression/aggregator.py:42-116 `CorrelationVolumeWarping.forward` with the shipped
+    recipe's flags (config/regression/mapfree/rot6d_trans_with_loftr.yaml:8-11: POSITION_ENCODER, MAX_SCORE_CHANNEL; no
+    dustbin / normalisation / CV layers):
+        C = softmax_j(vol0^T vol1)                      [B, HW, HW]  (6120^2 at the 360x270 map-free resolution)
+        vol1w = vol1 C^T ;  pos = grid C^T (grid = meshgrid(linspace(-1,1,H), linspace(-1,1,W)), 'ij')
+        out = cat[vol0, vol1w, pos, max_j C]            [B, 2D+3, H, W]
+    A flash-attention-shaped op (scores never need to be materialised): the oracle for next round's kernel."""
+    B, D, H, W = vol0.shape
+    v0, v1 = vol0.reshape(B, D, H * W), vol1.reshape(B, D, H * W)
+    c = torch.softmax(torch.bmm(v0.transpose(1, 2), v1), dim=2)
+    v1w = torch.bmm(v1, c.transpose(1, 2))
+    u = torch.linspace(-1, 1, H, dtype=vol0.dtype)
+    v = torch.linspace(-1, 1, W, dtype=vol0.dtype)
+    uu, vv = torch.meshgrid(u, v, indexing="ij")
+    grid = torch.stack([uu, vv], dim=0).reshape(2, H * W)[None].repeat(B, 1, 1)
+    pos = torch.bmm(grid, c.transpose(1, 2))
+    mx = c.max(dim=2, keepdim=True)[0].transpose(1, 2)
+    return torch.cat([v0, v1w, pos, mx], dim=1).reshape(B, -1, H, W)
+
+
 def rng(seed):
     return np.random.default_rng(seed)
 
