@@ -71,8 +71,8 @@ def linear(x, weight, bias=None, act=L.ACT_NONE, act_cols=-1, x2=None, engine=L.
     nws = lib.far_linear_workspace_bytes(M, N, Kt)
     ws = _ws(nws, x.device)
     with _timed("far_linear"):
-      check(lib.far_linear(ptr(x_), K1, K1, ptr(x2_), K2 if x2_ is not None else 0, K2, ptr(w), Kt, ptr(b), ptr(y), N,
-                         M, N, act, act_cols, engine, ptr(ws), ws.numel(), stream()), "far_linear")
+        check(lib.far_linear(ptr(x_), K1, K1, ptr(x2_), K2 if x2_ is not None else 0, K2, ptr(w), Kt, ptr(b), ptr(y), N,
+                           M, N, act, act_cols, engine, ptr(ws), ws.numel(), stream()), "far_linear")
     return y.reshape(*lead, N)
 
 
@@ -185,8 +185,8 @@ def linear_attention(q, k, v, eps=1e-6, feature_map_applied=False):
     ws = _ws(nws, q.device)
     C = H * D
     with _timed("far_linear_attention"):
-      check(lib.far_linear_attention(ptr(q_), C, ptr(k_), C, ptr(v_), C, ptr(out), C, N, Lq, S, H, D, float(eps),
-                                   int(feature_map_applied), ptr(ws), ws.numel(), stream()), "far_linear_attention")
+        check(lib.far_linear_attention(ptr(q_), C, ptr(k_), C, ptr(v_), C, ptr(out), C, N, Lq, S, H, D, float(eps),
+                                     int(feature_map_applied), ptr(ws), ws.numel(), stream()), "far_linear_attention")
     return out
 
 
@@ -203,8 +203,8 @@ def loftr_encoder_layer(x, source, weights, nhead, engine=L.ENGINE_AUTO):
     nws = lib.far_loftr_encoder_layer_workspace_bytes(N, Lq, S, C, nhead)
     ws = _ws(nws, x.device)
     with _timed("far_loftr_encoder_layer"):
-      check(lib.far_loftr_encoder_layer(ptr(x_), ptr(s_), ptr(out), N, Lq, S, C, nhead, byref(w), engine, ptr(ws),
-                                      ws.numel(), stream()), "far_loftr_encoder_layer")
+        check(lib.far_loftr_encoder_layer(ptr(x_), ptr(s_), ptr(out), N, Lq, S, C, nhead, byref(w), engine, ptr(ws),
+                                        ws.numel(), stream()), "far_loftr_encoder_layer")
     return out
 
 
@@ -223,9 +223,9 @@ def dual_softmax_match(feat_c0, feat_c1, hw0_c, hw1_c, thr, border_rm, temperatu
     cnt = torch.zeros(1, dtype=torch.int64, device=dev)
     conf = torch.empty((N, Lq, S), dtype=torch.float32, device=dev) if return_conf_matrix else None
     with _timed("far_dual_softmax_match_select"):
-      check(lib.far_dual_softmax_match_select(ptr(f0), ptr(f1), N, Lq, S, C, float(temperature), float(thr),
-                                            int(border_rm), hw0_c[0], hw0_c[1], hw1_c[0], hw1_c[1], ptr(conf),
-                                            ptr(cnt), engine, ptr(ws), nws, stream()), "far_dual_softmax_match_select")
+        check(lib.far_dual_softmax_match_select(ptr(f0), ptr(f1), N, Lq, S, C, float(temperature), float(thr),
+                                              int(border_rm), hw0_c[0], hw0_c[1], hw1_c[0], hw1_c[1], ptr(conf),
+                                              ptr(cnt), engine, ptr(ws), nws, stream()), "far_dual_softmax_match_select")
     M = int(cnt.item())  # the reference's sync point
     b_ids = torch.empty(M, dtype=torch.int64, device=dev)
     i_ids = torch.empty(M, dtype=torch.int64, device=dev)
@@ -264,11 +264,11 @@ def fine_preprocess(feat_f0, feat_f1, feat_c0, feat_c1, b_ids, i_ids, j_ids, W, 
     nws = lib.far_fine_preprocess_workspace_bytes(M, W * W, Cf, Cc)
     ws = _ws(nws, dev)
     with _timed("far_fine_preprocess"):
-      check(lib.far_fine_preprocess(ptr(feat_f0), ptr(feat_f1), sn, sc, sh, sw, Hf, Wf, Cf, ptr(c0), ptr(c1),
-                                  c0.shape[1], c1.shape[1], Cc, ptr(b_ids), ptr(i_ids), ptr(j_ids), M, W, stride,
-                                  w0c, w1c, ptr(f32c(down_w)), ptr(f32c(down_b)), ptr(f32c(merge_w)),
-                                  ptr(f32c(merge_b)), ptr(out0), ptr(out1), ptr(ws), ws.numel(), stream()),
-          "far_fine_preprocess")
+        check(lib.far_fine_preprocess(ptr(feat_f0), ptr(feat_f1), sn, sc, sh, sw, Hf, Wf, Cf, ptr(c0), ptr(c1),
+                                    c0.shape[1], c1.shape[1], Cc, ptr(b_ids), ptr(i_ids), ptr(j_ids), M, W, stride,
+                                    w0c, w1c, ptr(f32c(down_w)), ptr(f32c(down_b)), ptr(f32c(merge_w)),
+                                    ptr(f32c(merge_b)), ptr(out0), ptr(out1), ptr(ws), ws.numel(), stream()),
+            "far_fine_preprocess")
     return out0, out1
 
 
@@ -282,8 +282,8 @@ def fine_match(feat_f0, feat_f1, mkpts1_c, offset_scale):
     if M == 0:
         return expec, mk1f
     with _timed("far_fine_match"):
-      check(lib.far_fine_match(ptr(f32c(feat_f0)), ptr(f32c(feat_f1)), M, WW, C, ptr(f32c(mkpts1_c)),
-                             float(offset_scale), ptr(expec), ptr(mk1f), stream()), "far_fine_match")
+        check(lib.far_fine_match(ptr(f32c(feat_f0)), ptr(f32c(feat_f1)), M, WW, C, ptr(f32c(mkpts1_c)),
+                               float(offset_scale), ptr(expec), ptr(mk1f), stream()), "far_fine_match")
     return expec, mk1f
 
 
@@ -300,8 +300,8 @@ def eight_point(points1, points2, weights=None, counts=None):
     nws = lib.far_eight_point_workspace_bytes(P)
     ws = _ws(nws, p1.device)
     with _timed("far_eight_point"):
-      check(lib.far_eight_point(ptr(p1), ptr(p2), ptr(w), ptr(c), P, N, ptr(F), ptr(ws), ws.numel(), stream()),
-          "far_eight_point")
+        check(lib.far_eight_point(ptr(p1), ptr(p2), ptr(w), ptr(c), P, N, ptr(F), ptr(ws), ws.numel(), stream()),
+            "far_eight_point")
     return F
 
 
@@ -330,9 +330,9 @@ def pose_from_matches(mkpts0, mkpts1, mconf, offsets, K0, K1):
     nws = lib.far_eight_point_workspace_bytes(N)
     ws = _ws(nws, dev)
     with _timed("far_pose_from_matches"):
-      check(lib.far_pose_from_matches(ptr(f32c(mkpts0)), ptr(f32c(mkpts1)), ptr(f32c(mconf)), ptr(offsets), N,
-                                    ptr(f32c(K0)), ptr(f32c(K1)), ptr(E), ptr(Rt), ptr(npos), ptr(ws), ws.numel(),
-                                    stream()), "far_pose_from_matches")
+        check(lib.far_pose_from_matches(ptr(f32c(mkpts0)), ptr(f32c(mkpts1)), ptr(f32c(mconf)), ptr(offsets), N,
+                                      ptr(f32c(K0)), ptr(f32c(K1)), ptr(E), ptr(Rt), ptr(npos), ptr(ws), ws.numel(),
+                                      stream()), "far_pose_from_matches")
     return E, Rt, npos
 
 
@@ -389,8 +389,8 @@ def emm_bilinear_attn(qkv1, qkv2, pos, num_heads, scale, engine=L.ENGINE_AUTO):
     nws = lib.far_emm_bilinear_attn_workspace_bytes(B, N, num_heads, d)
     ws = _ws(nws, q1.device)
     with _timed("far_emm_bilinear_attn"):
-      check(lib.far_emm_bilinear_attn(ptr(q1), ptr(q2), ptr(p_), p_.shape[0], B, N, num_heads, d, float(scale), ptr(F1),
-                                    ptr(F2), engine, ptr(ws), ws.numel(), stream()), "far_emm_bilinear_attn")
+        check(lib.far_emm_bilinear_attn(ptr(q1), ptr(q2), ptr(p_), p_.shape[0], B, N, num_heads, d, float(scale), ptr(F1),
+                                      ptr(F2), engine, ptr(ws), ws.numel(), stream()), "far_emm_bilinear_attn")
     return F1, F2
 
 
@@ -405,8 +405,8 @@ def softmax_attention(qkv, num_heads, scale):
     nws = lib.far_softmax_attention_workspace_bytes(B, N, num_heads, d)
     ws = _ws(nws, q.device)
     with _timed("far_softmax_attention"):
-      check(lib.far_softmax_attention(ptr(q), B, N, num_heads, d, float(scale), ptr(out), ptr(ws), ws.numel(), stream()),
-          "far_softmax_attention")
+        check(lib.far_softmax_attention(ptr(q), B, N, num_heads, d, float(scale), ptr(out), ptr(ws), ws.numel(), stream()),
+            "far_softmax_attention")
     return out
 
 
