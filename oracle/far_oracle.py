@@ -745,6 +745,26 @@ def mapfree_correlation_aggregator(vol0, vol1):
     return torch.cat([v0, v1w, pos, mx], dim=1).reshape(B, -1, H, W)
 
 
+def torch_transformer_encoder(sd, x, num_layers=6, nhead=8, eps=1e-5):
+    """mapfree_6dreg/lib/models/regression/model.py:57-61,288-291: `nn.TransformerEncoder(nn.TransformerEncoderLayer(
+    d_model=256, nhead=8), num_layers=6)` in eval mode on [S, B, E] tokens (S = 12*9 = 108).  torch defaults: post-norm,
+    ReLU, dim_feedforward 2048, softmax(QK^T / sqrt(E/nhead)) self-attention with in_proj / out_proj biases.
+    `sd`: state dict of the nn.TransformerEncoder (keys layers.{i}.self_attn.in_proj_weight ...)."""
+    S, B, E = x.shape
+    hd = E // nhead
+    for i in range(num_layers):
+        p = _sub(sd, f"layers.{i}")
+        qkv = F.linear(x, p["self_attn.in_proj_weight"], p["self_attn.in_proj_bias"])
+        q, k, v = (t.reshape(S, B * nhead, hd).transpose(0, 1) for t in qkv.chunk(3, dim=-1))
+        att = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(hd), dim=-1) @ v           # [B*nhead, S, hd]
+        att = att.transpose(0, 1).reshape(S, B, E)
+        att = F.linear(att, p["self_attn.out_proj.weight"], p["self_attn.out_proj.bias"])
+        x = F.layer_norm(x + att, (E,), p["norm1.weight"], p["norm1.bias"], eps)
+        ff = F.linear(F.relu(F.linear(x, p["linear1.weight"], p["linear1.bias"])), p["linear2.weight"], p["linear2.bias"])
+        x = F.layer_norm(x + ff, (E,), p["norm2.weight"], p["norm2.bias"], eps)
+    return x
+
+
 def rng(seed):
     return np.random.default_rng(seed)
 
