@@ -64,6 +64,10 @@ _SIGS = {
     "far_pose_from_matches": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "far_prior_ransac_score": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, c_int, c_float, c_float, _P, _P, _P,
                                        _P, _P, _P]),
+    "far_segment_offsets": (c_int, [_P, c_longlong, c_int, _P, _P]),
+    "far_ransac_sample_models_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int]),
+    "far_ransac_sample_models": (c_int, [_P, _P, _P, c_longlong, c_int, _P, _P, _P, c_float, c_int, c_int,
+                                         ctypes.c_ulonglong, _P, _P, _P, c_size_t, _P]),
     "far_pose_from_essential_workspace_bytes": (c_size_t, [c_int]),
     "far_pose_from_essential": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "far_emm_bilinear_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
@@ -151,14 +155,16 @@ def stream():
 
 
 class _Workspace:
-    """Grow-only scratch buffer per device.  Ops on one stream run in order, so one buffer is enough; ops whose
-    workspace must survive until a later call (match select -> gather) take a private allocation instead."""
+    """Grow-only scratch buffer per (device, CUDA stream).  Ops issued on one stream run in order, so one buffer per
+    stream is enough; two streams (a side-stream prefetch, DataParallel threads with their own streams) never alias.
+    Ops whose workspace must survive until a later call (match select -> gather) take a private allocation instead."""
 
     def __init__(self):
         self.buf = {}
 
     def get(self, nbytes, device):
-        key = (device.type, device.index)
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream(device).cuda_stream)
         b = self.buf.get(key)
         if b is None or b.numel() < nbytes:
             b = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)

@@ -500,10 +500,12 @@ __global__ void __launch_bounds__(256) ransac_select_kernel(RaggedPts pts, int P
       float x0, y0, x1, y1, w;
       pts.load(pair, i, x0, y0, x1, y1, w);
       const float e = sampson_sq(E, x0, y0, x1, y1);
+      const int t1 = e <= inl_th / 10.0f ? 1 : 0, t2 = e <= inl_th / 100.0f ? 1 : 0;
       m = e <= inl_th ? 1 : 0;
       c0 += m;
-      c1 += e <= inl_th / 10.0f ? 1 : 0;
-      c2 += e <= inl_th / 100.0f ? 1 : 0;
+      c1 += t1;
+      c2 += t2;
+      m |= (unsigned char)((t1 << 1) | (t2 << 2));   // bit 0: inlier, bit 1: tight, bit 2: ultra tight (:279-283)
     }
     mask[(size_t)pts.off[pair] + i] = m;
   }
@@ -535,6 +537,186 @@ __global__ void __launch_bounds__(64) essential_to_cand_kernel(const float* __re
 #pragma unroll
   for (int k = 0; k < 9; ++k) { cand[(size_t)pair * 21 + k] = r1[k]; cand[(size_t)pair * 21 + 9 + k] = r2[k]; }
   cand[(size_t)pair * 21 + 18] = tt[0]; cand[(size_t)pair * 21 + 19] = tt[1]; cand[(size_t)pair * 21 + 20] = tt[2];
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Prior-guided RANSAC, sampling step + minimal solver (ransac.py:161-175 `sample`, :358-367 bias weights, :250-253
+// `estimate_model_from_minsample`), all on the device: no eager-torch math, no host sync, no [P, max_m] scatter.
+//   segment offsets      m_bids (sorted) -> offsets[P+1]                                      segment_offsets_kernel
+//   weights + CDF        w_i = exp(-symmetrical_epipolar(x0_i, x1_i, E_prior)/sigma^2) + 1e-4  (1 without a prior),
+//                        inclusive prefix sum per pair in fp64                                 ransac_cdf_kernel
+//   sample + 8-point     one thread per (pair, hypothesis): counter-based Philox4x32-10 keyed by (seed; pair, hyp),
+//                        inverse-CDF draws, the S sampled correspondences -> the 52-double moment record of
+//                        eightpt_accumulate (so eightpt_solve_kernel finishes the model)         ransac_sample_kernel
+// The reference draws with numpy's global RNG (np.random.choice(..., replace=True, p=w), or rand().topk without a
+// prior); bit-parity with that stream is meaningless, so the contract is: index k of hypothesis (p, h) is
+// searchsorted(cdf_p, u * cdf_p[-1], right) with u = philox(seed, p*H+h)[k] * 2^-32 -- reproducible, pinned by a numpy
+// Philox in the tests.  A draw that repeats an index already in the sample is redrawn (up to 4 times, next counter
+// block): duplicated correspondences make the 8-point system rank deficient.
+struct Philox {
+  uint32_t key0, key1;
+  __device__ __forceinline__ void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) const {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __device__ __forceinline__ void block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) const {
+    uint32_t c[4] = {c0, c1, c2, c3};
+    uint32_t k0 = key0, k1 = key1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      round(c, k0, k1);
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = c[i];
+  }
+};
+
+__global__ void segment_offsets_kernel(const long long* __restrict__ m_bids, long long M, int P,
+                                       long long* __restrict__ offsets) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > M) return;
+  // offsets[b] = first index whose batch id is >= b; thread i fills every b in (bid[i-1], bid[i]]
+  const long long lo = (i == 0) ? -1 : m_bids[i - 1];
+  const long long hi = (i == M) ? (long long)P : m_bids[i];
+  for (long long b = lo + 1; b <= hi && b <= P; ++b) offsets[b] = i;
+}
+
+__device__ __forceinline__ float sym_epipolar_sq(const float (&E)[9], float x0, float y0, float x1, float y1) {
+  const float lx = E[0] * x0 + E[1] * y0 + E[2], ly = E[3] * x0 + E[4] * y0 + E[5], lz = E[6] * x0 + E[7] * y0 + E[8];
+  const float mx = E[0] * x1 + E[3] * y1 + E[6], my = E[1] * x1 + E[4] * y1 + E[7];
+  const float num = x1 * lx + y1 * ly + lz;
+  return num * num * (1.f / (lx * lx + ly * ly) + 1.f / (mx * mx + my * my));
+}
+
+// one CTA (256 threads) per pair
+__global__ void __launch_bounds__(256) ransac_cdf_kernel(RaggedPts pts, int P, const float* __restrict__ prior_rt,
+                                                         float sigma_sq, double* __restrict__ cdf) {
+  __shared__ double warp_tot[8];
+  __shared__ double carry_s;
+  const int pair = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int n = pts.count(pair);
+  double* out = cdf + pts.off[pair];
+  float E[9];
+  const bool biased = prior_rt != nullptr;
+  if (biased) {  // E_prior = [t]_x R with the unit-norm translation of setup_prior (ransac.py:63-71,180)
+    const float* pr = prior_rt + (size_t)pair * 12;
+    const float tn = 1.f / fmaxf(sqrtf(pr[3] * pr[3] + pr[7] * pr[7] + pr[11] * pr[11]), 1e-12f);
+    const float tx = pr[3] * tn, ty = pr[7] * tn, tz = pr[11] * tn;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      E[j] = -tz * pr[4 + j] + ty * pr[8 + j];
+      E[3 + j] = tz * pr[j] - tx * pr[8 + j];
+      E[6 + j] = -ty * pr[j] + tx * pr[4 + j];
+    }
+  }
+  if (t == 0) carry_s = 0.0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 256) {
+    const int i = base + t;
+    double w = 0.0;
+    if (i < n) {
+      if (biased) {
+        float x0, y0, x1, y1, cf;
+        pts.load(pair, i, x0, y0, x1, y1, cf);
+        w = (double)(expf(-sym_epipolar_sq(E, x0, y0, x1, y1) / sigma_sq) + 1e-4f);
+        if (!(w == w)) w = 1e-4;  // degenerate prior (zero lines): keep a valid distribution
+      } else {
+        w = 1.0;
+      }
+    }
+    double v = w;  // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) warp_tot[wid] = v;
+    __syncthreads();
+    double pre = carry_s;
+    for (int k = 0; k < wid; ++k) pre += warp_tot[k];
+    if (i < n) out[i] = pre + v;
+    __syncthreads();
+    if (t == 255) carry_s = pre + v;
+    __syncthreads();
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(128) ransac_sample_kernel(RaggedPts pts, int P, int H, const double* __restrict__ cdf,
+                                                            unsigned long long seed, double* __restrict__ rec,
+                                                            int* __restrict__ idx_out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P * H) return;
+  const int pair = g / H;
+  const int n = pts.count(pair);
+  double* r = rec + (size_t)g * kRec;
+  if (n < S) {
+    r[51] = 0.0;
+    if (idx_out)
+      for (int k = 0; k < S; ++k) idx_out[(size_t)g * S + k] = -1;
+    return;
+  }
+  const double* c = cdf + pts.off[pair];
+  const double total = c[n - 1];
+  Philox rng{(uint32_t)seed, (uint32_t)(seed >> 32)};
+  int idx[S];
+  uint32_t u4[4];
+  int blk = 0, used = 4;
+  for (int k = 0; k < S; ++k) {
+    int pick = 0;
+    for (int attempt = 0; attempt < 5; ++attempt) {
+      if (used == 4) { rng.block((uint32_t)g, (uint32_t)blk, 0u, 0u, u4); ++blk; used = 0; }
+      const double target = ((double)u4[used++] * (1.0 / 4294967296.0)) * total;
+      int lo = 0, hi = n - 1;  // first i with cdf[i] > target  (searchsorted side='right')
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (c[mid] > target) hi = mid; else lo = mid + 1;
+      }
+      pick = lo;
+      bool dup = false;
+      for (int q = 0; q < k; ++q) dup |= (idx[q] == pick);
+      if (!dup) break;
+    }
+    idx[k] = pick;
+  }
+  if (idx_out)
+    for (int k = 0; k < S; ++k) idx_out[(size_t)g * S + k] = idx[k];
+  // the moment record of eightpt_accumulate_kernel for these S correspondences, unit weights (:253 passes ones)
+  float X1[S], Y1[S], X2[S], Y2[S];
+  double m1x = 0, m1y = 0, m2x = 0, m2y = 0;
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    float w;
+    pts.load(pair, idx[k], X1[k], Y1[k], X2[k], Y2[k], w);
+    m1x += X1[k]; m1y += Y1[k]; m2x += X2[k]; m2y += Y2[k];
+  }
+  m1x /= S; m1y /= S; m2x /= S; m2y /= S;
+  double a[45];
+#pragma unroll
+  for (int k = 0; k < 45; ++k) a[k] = 0.0;
+  double d1 = 0, d2 = 0;
+#pragma unroll 1
+  for (int k = 0; k < S; ++k) {
+    const double x1 = X1[k] - m1x, y1 = Y1[k] - m1y, x2 = X2[k] - m2x, y2 = Y2[k] - m2y;
+    d1 += sqrt(x1 * x1 + y1 * y1);
+    d2 += sqrt(x2 * x2 + y2 * y2);
+    const double X[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1.0};
+    int e = 0;
+#pragma unroll
+    for (int p = 0; p < 9; ++p)
+#pragma unroll
+      for (int q = p; q < 9; ++q) { a[e] = fma(X[p], X[q], a[e]); ++e; }
+  }
+#pragma unroll
+  for (int k = 0; k < 45; ++k) r[k] = a[k];
+  r[45] = m1x; r[46] = m1y; r[47] = m2x; r[48] = m2y;
+  r[49] = sqrt(2.0) / (d1 / S + 1e-8);
+  r[50] = sqrt(2.0) / (d2 / S + 1e-8);
+  r[51] = (double)S;
 }
 
 }  // namespace far
@@ -622,6 +804,43 @@ extern "C" int far_pose_from_essential(const float* mkpts0, const float* mkpts1,
   essential_to_cand_kernel<<<ceil_div(P, 64), 64, 0, st>>>(E, P, workspace);
   FAR_CHECK_LAUNCH();
   pose_select_kernel<<<ceil_div(P, 4), 128, 0, st>>>(pts, P, workspace, Rt, n_pos, mask);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+// ---- prior-guided RANSAC round, sampling + minimal solver ---------------------------------------------------------
+extern "C" int far_segment_offsets(const long long* m_bids, long long M, int P, long long* offsets, void* stream) {
+  FAR_REQUIRE(offsets && P >= 0 && M >= 0 && (M == 0 || m_bids));
+  const int blocks = (int)((M + 1 + 255) / 256);
+  segment_offsets_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(m_bids, M, P, offsets);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+extern "C" size_t far_ransac_sample_models_workspace_bytes(long long M, int P, int H) {
+  return (size_t)(M + 64) * 8 + (size_t)P * H * kRec * 8 + 512;
+}
+
+extern "C" int far_ransac_sample_models(const float* mkpts0, const float* mkpts1, const long long* offsets, long long M,
+                                        int P, const float* K0, const float* K1, const float* prior_rt,
+                                        float bias_sigma_sq, int H, int sample_size, unsigned long long seed,
+                                        float* models, int* sample_idx, float* workspace, size_t workspace_bytes,
+                                        void* stream) {
+  if (P <= 0 || H <= 0) return FAR_OK;
+  FAR_REQUIRE(offsets && K0 && K1 && models && workspace && sample_size == 8 && (M == 0 || (mkpts0 && mkpts1)) &&
+              (prior_rt == nullptr || bias_sigma_sq > 0.f));
+  if (workspace_bytes < far_ransac_sample_models_workspace_bytes(M, P, H)) return FAR_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  double* cdf = reinterpret_cast<double*>(base);
+  double* rec = cdf + (((size_t)M + 1 + 31) & ~size_t(31));
+  RaggedPts pts{mkpts0, mkpts1, nullptr, offsets, K0, K1};
+  ProfScope prof(PROF_SOLVER, 0.0, 0.0, st);
+  ransac_cdf_kernel<<<P, 256, 0, st>>>(pts, P, prior_rt, bias_sigma_sq, cdf);
+  FAR_CHECK_LAUNCH();
+  ransac_sample_kernel<8><<<ceil_div(P * H, 128), 128, 0, st>>>(pts, P, H, cdf, seed, rec, sample_idx);
+  FAR_CHECK_LAUNCH();
+  eightpt_solve_kernel<<<ceil_div(P * H, 64), 64, 0, st>>>(rec, P * H, models);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }

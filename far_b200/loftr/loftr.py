@@ -8,7 +8,6 @@ Differences that are deliberate and documented:
     with N == 1 every output has the reference's shape (`regressed_rt [1,9]`, `priorRT` numpy [3,4]).
   * `data['conf_matrix']` is None unless config['match_coarse']['materialize_conf_matrix'] is set.
 """
-import numpy as np
 import torch
 import torch.nn as nn
 
@@ -126,11 +125,18 @@ class LoFTR(nn.Module):
         if self.config['regress']['save_gating_weights']:
             data.update({'gating_reg_weights': pred_RT_wt})
         if self.config['solver'] == 'prior_ransac':  # loftr.py:187-192
-            rr = pred_RT.detach().cpu()
-            R = rotation_6d_to_matrix(rr[:, 3:] * pose_std_6d[3:] + pose_mean_6d[3:])
-            t = rr[:, :3] * pose_std_6d[:3] + pose_mean_6d[:3]
-            prior = torch.cat([R, t.unsqueeze(-1)], dim=-1).numpy()
-            data.update({'priorRT': prior[0] if prior.shape[0] == 1 else prior})
+            dev = pred_RT.device
+            rr = pred_RT.detach()
+            R = rotation_6d_to_matrix(rr[:, 3:] * pose_std_6d[3:].to(dev) + pose_mean_6d[3:].to(dev))
+            t = rr[:, :3] * pose_std_6d[:3].to(dev) + pose_mean_6d[:3].to(dev)
+            prior = torch.cat([R, t.unsqueeze(-1)], dim=-1)
+            data['priorRT_device'] = prior          # [N,3,4] on the device: what the batched GPU RANSAC round reads
+            # The reference hands spvs_RT a numpy [3,4] (a blocking D2H copy per head invocation).  Kept for the
+            # reference harness (PL_LoFTR.test_step -> spvs_RT); FarPosePipeline sets config['regress']
+            # ['prior_rt_on_device'] and never leaves the device.
+            if not self.config['regress'].get('prior_rt_on_device', False):
+                prior = prior.cpu().numpy()
+                data.update({'priorRT': prior[0] if prior.shape[0] == 1 else prior})
 
     def forward(self, data, train=False):
         self.forward_feature_extraction(data)

@@ -336,6 +336,37 @@ def pose_from_matches(mkpts0, mkpts1, mconf, offsets, K0, K1):
     return E, Rt, npos
 
 
+def segment_offsets(m_bids, P):
+    """offsets [P+1] int64 of the sorted batch ids m_bids [M] (replaces bincount + cumsum; one launch, no sync)."""
+    lib = L.load()
+    if not m_bids.is_cuda or m_bids.dtype != torch.int64:
+        raise L.FarError("segment_offsets: m_bids must be a CUDA int64 tensor")
+    m_bids = m_bids.contiguous()
+    off = torch.empty(P + 1, dtype=torch.int64, device=m_bids.device)
+    check(lib.far_segment_offsets(ptr(m_bids), int(m_bids.shape[0]), P, ptr(off), stream()), "far_segment_offsets")
+    return off
+
+
+def ransac_sample_models(mkpts0, mkpts1, offsets, K0, K1, prior_rt, bias_sigma_sq, H, seed, return_indices=False):
+    """RANSAC.sample + estimate_model_from_minsample (third_party/prior_ransac/ransac.py:161-175,250-253,358-367) for a
+    ragged batch: H minimal 8-point models per pair from (prior-biased or uniform) samples drawn on the device with a
+    counter-based Philox generator.  Returns models [P,H,3,3] (and sample indices [P,H,8] int32)."""
+    lib = L.load()
+    P = offsets.shape[0] - 1
+    dev = offsets.device
+    M = int(mkpts0.shape[0])
+    models = torch.empty((P, H, 3, 3), dtype=torch.float32, device=dev)
+    idx = torch.empty((P, H, 8), dtype=torch.int32, device=dev) if return_indices else None
+    pr = f32c(prior_rt) if prior_rt is not None else None
+    ws = _ws(lib.far_ransac_sample_models_workspace_bytes(M, P, H), dev)
+    with _timed("far_ransac_sample_models"):
+        check(lib.far_ransac_sample_models(ptr(f32c(mkpts0)), ptr(f32c(mkpts1)), ptr(offsets), M, P, ptr(f32c(K0)),
+                                           ptr(f32c(K1)), ptr(pr), float(bias_sigma_sq), H, 8,
+                                           int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(models), ptr(idx), ptr(ws), ws.numel(),
+                                           stream()), "far_ransac_sample_models")
+    return (models, idx) if return_indices else models
+
+
 def prior_ransac_score(mkpts0, mkpts1, offsets, K0, K1, models, prior_rt, pcl, prior_lambda, inl_th):
     """RANSAC.get_prior_estimate + verify + remove_bad_models (third_party/prior_ransac/ransac.py:203-231,256-292,
     303-308) for every pair of a ragged batch.  models [P,H,3,3]; prior_rt [P,3,4] or None; pcl [npcl,3].

@@ -2,54 +2,62 @@
 (mp3d_loftr/src/lightning/lightning_loftr.py:325-421), run as N independent B=1 evaluations in one pass.
 
     LoFTR.forward                       backbone (cuDNN) -> coarse transformer -> dual-softmax matching -> fine level
-    estimate_pose_batched               weighted normalised 8-point + cheirality (R,t)   [reference: OpenCV RANSAC on CPU
-                                        in a python loop with 3 PCIe hops; here on-device, SURVEY.md 8d config 2]
+    solver call 1                       RANSAC round on the GPU, uniform sampling, no prior (the reference's
+                                        `prior_ransac_noprior` branch, metrics.py:124-143; OpenCV RANSAC on the CPU in a
+                                        python loop with 3 PCIe hops in the shipped recipe)
     for i in range(fine_pred_steps):    FAR head: LoFTR regress layers -> EMM bilinear attention -> gated MLP fusion
-        forward_rt_prediction           (the prior-guided 2nd RANSAC round between the two invocations is SURVEY.md
-        estimate_pose_batched            8f rank 2 "next"; the solver is simply re-run so the per-pair work of the
-                                         recipe of record is preserved)
+        forward_rt_prediction
+        solver call 2 (i == 0)          prior-guided RANSAC round with the head's pose as the prior
+                                        (lightning_loftr.py:343-344, metrics.py:100-123)
+
+The counters the head's gate consumes (`num_correspondences_after_ransac`, `inliers_best_tight`,
+`inliers_best_ultra_tight`) are RANSAC inlier counts in both solver calls, the quantity the gate was trained on.
+`first_solver='weighted_8pt'` selects SURVEY.md 8d config 2's literal solver instead (one mconf-weighted 8-point fit,
+no outlier rejection: its `after_ransac` counter is the cheirality vote, NOT an inlier count -- for solver benchmarks,
+not for real checkpoints).
 """
 import torch
 
-from .solver import estimate_pose_batched
+from .solver import estimate_pose_batched, estimate_pose_ransac_batched
 from .loftr.pose import pose_mean_6d, pose_std_6d, rotation_6d_to_matrix
 
 
 class FarPosePipeline:
-    def __init__(self, model, K0, K1, fine_pred_steps=None, prior_ransac=False, ransac_kwargs=None):
+    def __init__(self, model, K0, K1, fine_pred_steps=None, prior_ransac=True, ransac_kwargs=None,
+                 first_solver='ransac'):
         self.model = model
         self.K0, self.K1 = K0, K1
         self.steps = fine_pred_steps if fine_pred_steps is not None else model.config.get('fine_pred_steps', 1)
         # prior_ransac=True: the solver call between the two head invocations is the prior-guided RANSAC round of the
-        # recipe of record (lightning_loftr.py:343-344, metrics.py:100-123) run on the GPU (far_b200/ransac.py) with the
-        # first head prediction as the prior, instead of a plain re-run of the weighted 8-point solver.
+        # recipe of record run on the GPU (far_b200/ransac.py) with the first head prediction as the prior;
+        # False: the first solver is simply re-run.
         self.prior_ransac = prior_ransac
+        self.first_solver = first_solver
         self.ransac_kwargs = ransac_kwargs or {}
+        if 'regress' in model.config:
+            model.config['regress']['prior_rt_on_device'] = True   # no blocking D2H of the prior (loftr.py:187-192)
+
+    def _solve(self, data, K0, K1, prior=None):
+        if self.first_solver == 'weighted_8pt' and prior is None:
+            return estimate_pose_batched(data, K0, K1)
+        return estimate_pose_ransac_batched(data, K0, K1, prior, **self.ransac_kwargs)
 
     @torch.no_grad()
     def __call__(self, image0, image1):
         """image0/1: [N,1,H,W] fp32 CUDA in [0,1].  Returns dict: pose [N,3,4] fused (R|t), regressed_rt [N,9],
-        loftr_rt [N,3,4], num_matches [N], gating [N,2]."""
+        loftr_rt [N,3,4], num_matches [N] (before RANSAC), num_inliers [N] (after RANSAC), gating [N,2]."""
         m = self.model
         data = {'image0': image0, 'image1': image1}
         m(data)
         N = image0.shape[0]
         K0 = self.K0[:N] if self.K0.shape[0] >= N else self.K0.expand(N, 3, 3)
         K1 = self.K1[:N] if self.K1.shape[0] >= N else self.K1.expand(N, 3, 3)
-        estimate_pose_batched(data, K0, K1)
+        self._solve(data, K0, K1)
         if m.config.get('regress_rt'):
             for i in range(self.steps):
                 m.forward_rt_prediction(data)
                 if i == 0 and self.steps > 1:
-                    if self.prior_ransac:
-                        from .ransac import prior_ransac_round
-                        rr0 = data['regressed_rt']
-                        d0 = rr0.device
-                        R0 = rotation_6d_to_matrix(rr0[:, 3:] * pose_std_6d[3:].to(d0) + pose_mean_6d[3:].to(d0))
-                        t0 = rr0[:, :3] * pose_std_6d[:3].to(d0) + pose_mean_6d[:3].to(d0)
-                        prior_ransac_round(data, K0, K1, torch.cat([R0, t0.unsqueeze(-1)], dim=-1), **self.ransac_kwargs)
-                    else:
-                        estimate_pose_batched(data, K0, K1)
+                    self._solve(data, K0, K1, data['priorRT_device'] if self.prior_ransac else None)
             rr = data['regressed_rt']
             dev = rr.device
             R = rotation_6d_to_matrix(rr[:, 3:] * pose_std_6d[3:].to(dev) + pose_mean_6d[3:].to(dev))
@@ -59,6 +67,7 @@ class FarPosePipeline:
             pose = data['loftr_rt']
         return {'pose': pose, 'regressed_rt': data.get('regressed_rt'), 'loftr_rt': data['loftr_rt'],
                 'num_matches': data['num_correspondences_before_ransac'],
+                'num_inliers': data['num_correspondences_after_ransac'],
                 'gating': data.get('gating_reg_weights'), 'data': data}
 
 

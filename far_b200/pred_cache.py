@@ -88,5 +88,13 @@ def load_batch(parent, split, pair_ids, device='cpu'):
 
 def from_pipeline(out):
     """FarPosePipeline output -> (loftr_preds [N,4,4] float64, loftr_num_corr [N]) for ViTEss.forward, on the device
-    the poses live on (BASELINE configs[2]: "8pt-ViT + cached-correspondence solver" fed from the same run)."""
-    return to_vit_convention(out['loftr_rt']), out['num_matches'].to(torch.int64)
+    the poses live on (BASELINE configs[2]: "8pt-ViT + cached-correspondence solver" fed from the same run).  The
+    count is `num_correspondences_after_ransac`, the quantity the reference's cache writer stores
+    (lightning_loftr.py:356-359), so the in-memory path and save_batch -> load_batch give the same tensors."""
+    return to_vit_convention(out['loftr_rt']), out['num_inliers'].to(torch.int64)
+
+
+def save_pipeline(parent, split, pair_ids, out):
+    """Write a FarPosePipeline output in the reference's on-disk format (poses = the solver's loftr_rt, counts =
+    num_correspondences_after_ransac; lightning_loftr.py:348-360)."""
+    save_batch(parent, split, pair_ids, out['loftr_rt'], out['num_inliers'])

@@ -10,25 +10,37 @@ What `estimate_pose(..., solver='prior_ransac', priorRT=...)` does for ONE pair 
     verify           Sampson inliers at 3 thresholds, argmax(inliers + prior score)       :256-292
     pose             cv2.recoverPose on the winner                                         metrics.py:164-170
 
-here runs for all pairs of the batch at once on the device: sampling with `torch.multinomial`, the minimal solver is the
-in-repo normalised 8-point on 8 correspondences (`far_eight_point`; the recipe's `essential_cv2` model calls OpenCV's
-5-point solver 2048 times per pair on the CPU -- un-vendored arithmetic), scoring and selection in
-`far_prior_ransac_score`, candidate selection by the cheirality vote of `far_pose_from_essential` over the inliers.
-Sampling is stochastic (as in the reference): parity is pinned on the deterministic scoring step
-(tests/golden/ransac.npz, produced by the unmodified `RANSAC.verify` / `get_prior_estimate`).
+here runs for all pairs of the batch at once, entirely on the device, as THREE C-ABI calls with no torch math and no
+host synchronisation in between:
+
+    far_ransac_sample_models   bias weights + per-pair CDF + Philox inverse-CDF sampling + the in-repo normalised
+                               8-point on each 8-sample (the recipe's `essential_cv2` model calls OpenCV's 5-point
+                               solver 2048 times per pair on the CPU -- un-vendored arithmetic)
+    far_prior_ransac_score     prior score, Sampson inliers, argmax, masks and the 3 counters
+    far_pose_from_essential    cheirality vote over the inliers (cv2.recoverPose's criterion)
+
+(plus `far_segment_offsets` to turn the sorted `m_bids` into segment offsets).  Without a prior
+(`prior_rt=None`) the same round is the reference's `solver='prior_ransac_noprior'` branch (metrics.py:124-143):
+uniform sampling, inlier count only.  Sampling is stochastic in the reference (numpy's global RNG); here it is a
+counter-based generator keyed by (seed, pair, hypothesis), so the samples are reproducible and pinned by a numpy
+Philox in tests/test_gpu_ransac.py; the deterministic scoring step is pinned to the unmodified
+`RANSAC.verify` / `get_prior_estimate` (tests/golden/ransac.npz).
 """
 import torch
 
 from . import ops
 
+_PCL = {}
 
-def _skew_times_R(rt):
-    """E_prior = [t]_x R of a [N,3,4] pose (ransac.py:63-71 `fundamental_from_RT`, which returns E)."""
-    R, t = rt[:, :, :3], rt[:, :, 3]
-    z = torch.zeros_like(t[:, 0])
-    tx = torch.stack([torch.stack([z, -t[:, 2], t[:, 1]], -1), torch.stack([t[:, 2], z, -t[:, 0]], -1),
-                      torch.stack([-t[:, 1], t[:, 0], z], -1)], -2)
-    return tx @ R
+
+def default_pcl(device, seed=0):
+    """metrics.py:103: 300 points uniform in [-3, 3]^3 (the reference redraws them per call with numpy's RNG; a fixed,
+    seeded cloud per device keeps the round deterministic and costs no launch)."""
+    key = (str(device), seed)
+    if key not in _PCL:
+        g = torch.Generator().manual_seed(20240000 + seed)
+        _PCL[key] = (torch.rand(300, 3, generator=g) * 6.0 - 3.0).to(device)
+    return _PCL[key]
 
 
 def normalise_prior(prior_rt):
@@ -38,66 +50,44 @@ def normalise_prior(prior_rt):
     return p
 
 
-def bias_weights(kp0, kp1, m_bids, prior_rt, sigma_sq=0.1):
-    """exp(-symmetrical_epipolar_distance / sigma^2) per match (ransac.py:358-367, use_linear_bias_sampling)."""
-    E = _skew_times_R(prior_rt)[m_bids]                                       # [M,3,3]
-    p0 = torch.cat([kp0, torch.ones_like(kp0[:, :1])], 1)
-    p1 = torch.cat([kp1, torch.ones_like(kp1[:, :1])], 1)
-    l = torch.einsum('mij,mj->mi', E, p0)                                      # E p0: line in image 1
-    m = torch.einsum('mji,mj->mi', E, p1)                                      # E^T p1
-    num = (p1 * l).sum(-1) ** 2
-    d = num * (1.0 / (l[:, 0] ** 2 + l[:, 1] ** 2) + 1.0 / (m[:, 0] ** 2 + m[:, 1] ** 2))
-    return torch.exp(-d / sigma_sq)
+@torch.no_grad()
+def ransac_round(mkpts0, mkpts1, m_bids, K0, K1, prior_rt=None, batch_size=2048, inl_th=3e-7, prior_lambda=0.3,
+                 bias_sigma_sq=0.1, biased=True, pcl=None, seed=0, offsets=None):
+    """One (prior-guided) RANSAC round for every pair of a ragged batch.  mkpts* [M,2] pixel keypoints, m_bids [M]
+    sorted pair ids, K0/K1 [N,3,3], prior_rt [N,3,4] or None.  Returns a dict of device tensors:
+    Rt [N,3,4], E [N,3,3], mask [M] uint8 (bit 0 inlier / 1 tight / 2 ultra tight), counts3 [N,3] int32, best [N],
+    scores [N,H], counts [N] (matches per pair), n_pos [N]."""
+    dev = mkpts0.device
+    N = K0.shape[0]
+    K0, K1 = K0.to(dev).float().contiguous(), K1.to(dev).float().contiguous()
+    if offsets is None:
+        offsets = ops.segment_offsets(m_bids, N)
+    prior = prior_rt.to(dev).float().contiguous() if prior_rt is not None else None
+    models = ops.ransac_sample_models(mkpts0, mkpts1, offsets, K0, K1, prior if biased else None, bias_sigma_sq,
+                                      batch_size, seed)
+    if prior is not None and pcl is None:
+        pcl = default_pcl(dev)
+    scores, best, best_E, counts3, mask = ops.prior_ransac_score(mkpts0, mkpts1, offsets, K0, K1, models, prior, pcl,
+                                                                 prior_lambda, inl_th)
+    Rt, npos = ops.pose_from_essential(mkpts0, mkpts1, mask, offsets, K0, K1, best_E)
+    return {'Rt': Rt, 'E': best_E, 'mask': mask, 'counts3': counts3, 'best': best, 'scores': scores,
+            'offsets': offsets, 'n_pos': npos}
 
 
 @torch.no_grad()
 def prior_ransac_round(data, K0, K1, prior_rt, batch_size=2048, inl_th=3e-7, prior_lambda=0.3, bias_sigma_sq=0.1,
-                       biased=True, pcl=None, generator=None):
-    """One prior-guided RANSAC round for every pair of the batch.  Reads m_bids, mkpts0_f, mkpts1_f from `data`;
-    prior_rt [N,3,4] (e.g. the FAR head's prediction, loftr.py:187-192).  Writes the same keys estimate_pose_batched
-    writes (loftr_rt, num_correspondences*, inliers_best_tight / ultra_tight) and returns loftr_rt [N,3,4]."""
-    mk0, mk1, m_bids = data['mkpts0_f'], data['mkpts1_f'], data['m_bids']
-    dev = mk0.device
-    N = K0.shape[0]
-    K0, K1 = K0.to(dev).float(), K1.to(dev).float()
-    M = int(mk0.shape[0])
-    counts = torch.bincount(m_bids, minlength=N)
-    offsets = torch.zeros(N + 1, dtype=torch.int64, device=dev)
-    offsets[1:] = torch.cumsum(counts, 0)
-    prior = normalise_prior(prior_rt.to(dev)) if prior_rt is not None else None
-    if pcl is None:  # metrics.py:103: 300 points uniform in [-3, 3]^3
-        pcl = torch.rand(300, 3, device=dev, generator=generator) * 6.0 - 3.0
-    if M == 0:
-        eye = torch.eye(3, 4, device=dev).repeat(N, 1, 1)
-        zero = torch.zeros(N, dtype=torch.int64, device=dev)
-        data.update({'loftr_rt': eye, 'expec_rt': eye, 'num_correspondences_before_ransac': counts,
-                     'num_correspondences_after_ransac': zero, 'num_correspondences': zero,
-                     'inliers_best_tight': zero, 'inliers_best_ultra_tight': zero})
-        return eye
-    # K-normalised keypoints (metrics.py:88-89)
-    k0, k1 = K0[m_bids], K1[m_bids]
-    kp0 = (mk0 - k0[:, :2, 2]) / torch.stack([k0[:, 0, 0], k0[:, 1, 1]], -1)
-    kp1 = (mk1 - k1[:, :2, 2]) / torch.stack([k1[:, 0, 0], k1[:, 1, 1]], -1)
-    # sampling weights, padded to [N, max matches]
-    w = bias_weights(kp0, kp1, m_bids, prior, bias_sigma_sq) + 1e-4 if (biased and prior is not None) \
-        else torch.ones(M, device=dev)
-    max_m = int(counts.max())                       # one host sync (the reference round-trips through numpy here)
-    local = torch.arange(M, device=dev) - offsets[m_bids]
-    W = torch.zeros(N, max(max_m, 1), device=dev)
-    W[m_bids, local] = w
-    W[counts < 8, 0] = 1.0                          # pairs that cannot be solved still need a valid distribution
-    idx = torch.multinomial(W, batch_size * 8, replacement=True, generator=generator)      # [N, H*8] local indices
-    gidx = (idx + offsets[:N, None]).clamp_(max=M - 1)
-    p0 = kp0[gidx].reshape(N * batch_size, 8, 2)
-    p1 = kp1[gidx].reshape(N * batch_size, 8, 2)
-    models = ops.eight_point(p0, p1, None).reshape(N, batch_size, 3, 3)
-    scores, best, best_E, counts3, mask = ops.prior_ransac_score(mk0, mk1, offsets, K0, K1, models, prior, pcl,
-                                                                 prior_lambda, inl_th)
-    Rt, npos = ops.pose_from_essential(mk0, mk1, mask, offsets, K0, K1, best_E)
-    c3 = counts3.to(torch.int64)
-    data.update({'loftr_rt': Rt, 'expec_rt': Rt, 'expec_e': best_E, 'ransac_inlier_mask': mask.bool(),
-                 'ransac_best_index': best, 'ransac_scores': scores,
-                 'num_correspondences_before_ransac': counts,
+                       biased=True, pcl=None, seed=0):
+    """The round applied to a LoFTR `data` dict: reads m_bids, mkpts0_f, mkpts1_f; prior_rt [N,3,4] (e.g. the FAR
+    head's prediction, loftr.py:187-192) or None for the reference's `prior_ransac_noprior` round.  Writes the keys
+    spvs_RT writes (supervision.py:226-233: loftr_rt, num_correspondences*, inliers_best_tight / ultra_tight) with the
+    reference's meaning -- `num_correspondences_after_ransac` IS the RANSAC inlier count -- and returns loftr_rt."""
+    r = ransac_round(data['mkpts0_f'], data['mkpts1_f'], data['m_bids'], K0, K1, prior_rt, batch_size, inl_th,
+                     prior_lambda, bias_sigma_sq, biased, pcl, seed)
+    off = r['offsets']
+    c3 = r['counts3'].to(torch.int64)
+    data.update({'loftr_rt': r['Rt'], 'expec_rt': r['Rt'], 'expec_e': r['E'], 'ransac_inlier_mask': r['mask'],
+                 'ransac_best_index': r['best'], 'ransac_scores': r['scores'],
+                 'num_correspondences_before_ransac': off[1:] - off[:-1],
                  'num_correspondences_after_ransac': c3[:, 0], 'num_correspondences': c3[:, 0],
                  'inliers_best_tight': c3[:, 1], 'inliers_best_ultra_tight': c3[:, 2]})
-    return Rt
+    return r['Rt']

@@ -192,11 +192,34 @@ int far_pose_from_matches(const float* mkpts0, const float* mkpts1, const float*
  *                 prior_rt == NULL: no prior term)
  *   -inf for degenerate models (min |diag E| <= 1e-4, ransac.py:303-308) and for pairs with < 8 matches.
  * Then per pair: best_idx = argmax_h (lowest index on ties; -1 if none), best_E [P,3,3], counts3 [P,3] = inliers of the
- * winner at inl_th, inl_th/10, inl_th/100 (:279-283), inlier_mask [M] (uint8) at inl_th. */
+ * winner at inl_th, inl_th/10, inl_th/100 (:279-283), inlier_mask [M] (uint8): bit 0 = inlier at inl_th, bit 1 = at
+ * inl_th/10 (`inliers_best_tight`), bit 2 = at inl_th/100 (`inliers_best_ultra_tight`). */
 int far_prior_ransac_score(const float* mkpts0, const float* mkpts1, const long long* offsets, int P, const float* K0,
                            const float* K1, const float* models, int H, const float* prior_rt, const float* pcl,
                            int npcl, float prior_lambda, float inl_th, float* scores, int* best_idx, float* best_E,
                            int* counts3, unsigned char* inlier_mask, void* stream);
+/* ---- prior-guided RANSAC round, sampling + minimal solver (no eager-torch math, no host sync) -----------------------
+ * far_segment_offsets: m_bids [M] int64, sorted ascending (what get_coarse_match yields, coarse_matching.py:193) ->
+ *   offsets [P+1] int64 with offsets[b] = first match of pair b (replaces bincount + cumsum).
+ * far_ransac_sample_models: for every pair p and hypothesis h < H draws `sample_size` (= 8) correspondences of the
+ *   pair's segment and solves the minimal model with the in-repo normalised 8-point (cv_geometry.py:772-833, unit
+ *   weights as ransac.py:250-253) -> models [P,H,3,3].  Sampling distribution (ransac.py:161-175, :358-367):
+ *     prior_rt != NULL: p_i ~ exp(-symmetrical_epipolar_distance(x0_i, x1_i, [t]_x R) / bias_sigma_sq) + 1e-4 with the
+ *                       prior translation normalised to unit length (`use_linear_bias_sampling`, 'biased');
+ *     prior_rt == NULL: uniform.
+ *   Draw k of (p,h) = searchsorted(cdf_p, u * cdf_p[-1], 'right'), u = Philox4x32-10(key = seed; counter = (p*H+h,
+ *   block, 0, 0))[k mod 4] * 2^-32, blocks consumed in order; an index already in the sample is redrawn (at most 4
+ *   times).  The reference uses numpy's global RNG there, so only the distribution is the contract; the counter-based
+ *   generator makes samples reproducible and testable.  sample_idx [P,H,8] int32 (segment-local; -1 for pairs with
+ *   fewer than 8 matches) may be NULL.  Pairs with < 8 matches get all-zero models (rejected by the scoring step).
+ *   The recipe of record's minimal solver is OpenCV's 5-point through cv2.findEssentialMat(LMEDS) on 6 points
+ *   (cv_geometry.py:836-859), un-vendored arithmetic: the in-repo 8-point is the minimal solver here. */
+int far_segment_offsets(const long long* m_bids, long long M, int P, long long* offsets, void* stream);
+size_t far_ransac_sample_models_workspace_bytes(long long M, int P, int H);
+int far_ransac_sample_models(const float* mkpts0, const float* mkpts1, const long long* offsets, long long M, int P,
+                             const float* K0, const float* K1, const float* prior_rt, float bias_sigma_sq, int H,
+                             int sample_size, unsigned long long seed, float* models, int* sample_idx,
+                             float* workspace, size_t workspace_bytes, void* stream);
 /* (R | t) [P,3,4] of essential matrices E [P,3,3] by the cheirality vote of far_pose_from_matches (the criterion of
  * cv2.recoverPose, metrics.py:164-170) over the matches with mask != 0 (mask NULL: all); E == 0 -> identity pose. */
 size_t far_pose_from_essential_workspace_bytes(int P);

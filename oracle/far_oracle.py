@@ -723,6 +723,50 @@ def ransac_verify(kp1, kp2, models, inl_th, prior_score):
     return best, score, masks
 
 
+def philox4x32_10(key, c0, c1=0, c2=0, c3=0):
+    """Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11): counter block -> 4 uint32.
+    Vectorised over c0 (numpy uint64 arithmetic).  `key` = 64-bit seed (low word key0, high word key1)."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    mask = np.uint64(0xFFFFFFFF)
+    c = [np.asarray(x, dtype=np.uint64) & mask for x in np.broadcast_arrays(c0, c1, c2, c3)]
+    k0, k1 = key & 0xFFFFFFFF, (key >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = [hi1 ^ c[1] ^ np.uint64(k0), lo1, hi0 ^ c[3] ^ np.uint64(k1), lo0]
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return np.stack(c, -1).astype(np.uint64)
+
+
+def ransac_sample_indices(weights, H, seed, pair=0, S=8):
+    """The sampling contract of far_ransac_sample_models (include/far_sm100.h): for hypothesis h of pair `pair`,
+    draw k = searchsorted(cumsum(w), u * sum(w), 'right') with u = philox(seed; (pair*H+h, block, 0, 0))[j] * 2^-32,
+    consuming the 4 words of a block in order and a new block when they run out; a draw that repeats an index already
+    in the sample is redrawn, at most 4 times.  The distribution is the reference's np.random.choice(p = w / sum w)
+    (ransac.py:161-175); the generator is ours.  weights: fp64 numpy [n] (already including the +1e-4).  -> [H,S]."""
+    cdf = np.cumsum(np.asarray(weights, dtype=np.float64))
+    n = cdf.shape[0]
+    out = np.full((H, S), -1, dtype=np.int64)
+    if n < S:
+        return out
+    for h in range(H):
+        g = pair * H + h
+        blk, used, words = 0, 4, None
+        for k in range(S):
+            pick = 0
+            for _ in range(5):
+                if used == 4:
+                    words = philox4x32_10(seed, g, blk)
+                    blk, used = blk + 1, 0
+                target = (float(words[used]) / 4294967296.0) * cdf[-1]
+                used += 1
+                pick = min(int(np.searchsorted(cdf, target, side='right')), n - 1)
+                if pick not in out[h, :k]:
+                    break
+            out[h, k] = pick
+    return out
+
+
 # --------------------------------------------------------------------------------------- 8f rank 3: map-free aggregator
 def mapfree_correlation_aggregator(vol0, vol1):
     """mapfree_6dreg/lib/models/regression/aggregator.py:42-116 `CorrelationVolumeWarping.forward` with the shipped

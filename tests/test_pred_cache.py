@@ -73,15 +73,23 @@ def test_batch_and_in_memory_paths(tmp_path):
     Rm = T_mem[:, :3, :3]
     assert torch.allclose(Rm @ Rm.transpose(1, 2), torch.eye(3, dtype=torch.float64).expand(4, 3, 3), atol=1e-6)
     assert torch.allclose(torch.linalg.det(Rm), torch.ones(4, dtype=torch.float64), atol=1e-6)
-    out = {'loftr_rt': poses.float(), 'num_matches': counts}
+    # the in-memory path feeds ViTEss what the disk path would: poses = loftr_rt, count = AFTER-RANSAC inliers
+    # (lightning_loftr.py:356-359), not the pre-RANSAC match count
+    out = {'loftr_rt': poses.float(), 'num_matches': counts + 1000, 'num_inliers': counts}
     lp, n = pred_cache.from_pipeline(out)
-    assert torch.equal(lp, T_mem) and n.dtype == torch.int64
+    assert torch.equal(lp, T_mem) and n.dtype == torch.int64 and torch.equal(n, counts)
+    pred_cache.save_pipeline(parent, 'mem', [0, 1, 2, 3], out)
+    T2, nc2 = pred_cache.load_batch(parent, 'mem', [0, 1, 2, 3])
+    assert torch.equal(T2, lp) and torch.equal(nc2, n)
 
 
-def test_ransac_host_glue_vs_reference_golden(golden_dir):
-    """The torch glue of far_b200/ransac.py that needs no GPU: prior normalisation (setup_prior, ransac.py:176-186) and
-    the sampling bias weights (ransac.py:358-367) against the fixture produced by the unmodified reference."""
-    from far_b200.ransac import bias_weights, normalise_prior
+def test_ransac_host_glue_and_sampling_contract(golden_dir):
+    """Host-side pieces of the RANSAC round that need no GPU: prior normalisation (setup_prior, ransac.py:176-186), the
+    oracle's bias weights against the fixture produced by the unmodified reference (ransac.py:358-367), and the
+    counter-based sampling contract (Philox4x32-10 known answers of the Random123 distribution; distinct indices;
+    draws follow the weights)."""
+    from far_b200.ransac import normalise_prior
+    from oracle import far_oracle as O
     g = np.load(os.path.join(golden_dir, "ransac.npz"))
     kp1, kp2 = torch.from_numpy(g["kp1"]), torch.from_numpy(g["kp2"])
     prior = torch.from_numpy(g["prior_rt"])[None].clone()
@@ -89,5 +97,15 @@ def test_ransac_host_glue_vs_reference_golden(golden_dir):
     pn = normalise_prior(prior)
     assert torch.allclose(pn[0, :, 3].norm(), torch.tensor(1.0), atol=1e-6)
     assert torch.allclose(pn[0], torch.from_numpy(g["prior_rt"]), atol=1e-6)
-    bw = bias_weights(kp1, kp2, torch.zeros(kp1.shape[0], dtype=torch.int64), pn, 0.1)
+    bw = O.ransac_bias_weight(kp1, kp2, pn[0], 0.1)
     assert (bw - torch.from_numpy(g["bias_ref"])).abs().max() < 1e-5
+    assert [int(x) for x in O.philox4x32_10(0, 0)] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert [int(x) for x in O.philox4x32_10(0xffffffffffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff)] == \
+        [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    w = bw.double().numpy() + 1e-4
+    idx = O.ransac_sample_indices(w, 512, seed=3)
+    assert idx.min() >= 0 and idx.max() < w.shape[0] and all(len(set(r.tolist())) == 8 for r in idx)
+    mass = np.bincount(idx.reshape(-1), minlength=w.shape[0]) / idx.size
+    top = np.argsort(-w)[: w.shape[0] // 10]
+    assert abs(mass[top].sum() - w[top].sum() / w.sum()) < 0.05
+    assert (O.ransac_sample_indices(np.ones(5), 4, seed=3) == -1).all()
