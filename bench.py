@@ -1,19 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- image-pairs/sec of the FAR per-pair pose hot path at 640x480 (BASELINE.json metric).
+"""bench.py -- image-pairs/sec of the FAR per-pair pose hot path (BASELINE.json metric).
 
-  python bench.py --gpus 1 --steps K --warmup W            our arm (CUDA path through the C ABI)
-  python bench.py --impl reference --gpus N ...            the reference arm: the CPU restatement of the reference
-                                                           (oracle/far_oracle.py; the reference is pure Python and
-                                                           cannot travel to the GPU box) on the host cores
-  torchrun --nproc-per-node N bench.py --gpus N ...        one rank per GPU; pairs shard across ranks (weak scaling)
+  python bench.py --gpus 1 --steps K --warmup W [--workload W]   our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N ...                  the reference arm: the CPU restatement of the reference
+                                                                 (oracle/far_oracle.py; the reference is pure Python and
+                                                                 cannot travel to the GPU box) on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...              one rank per GPU; pairs shard across ranks
 
-A "step" = one pass of the whole path over one batch of synthetic pairs:
-  workload `mp3d_loftr_far` (BASELINE.json configs[1]): FAR-LoFTR forward (ResNet-FPN backbone -> 3x(self,cross)
-  linear-attention layers -> dual-softmax coarse matching -> 5x5 fine level) -> weighted 8-point + cheirality
-  -> FAR head (regress LoFTR layers -> EMM dual-softmax bilinear attention -> gated pose MLP) -> prior-guided RANSAC
-  round (2048 hypotheses / pair, the head's pose as prior) -> FAR head again (gate + blend), batch 32 pairs,
-  random-init (seeded) weights, thr = 0 so random features still produce ~1.1k matches/pair.
-Prints ONE JSON line (rank 0).
+Workloads (BASELINE.json configs; a "step" = one pass of the path over one batch of synthetic pairs):
+  mp3d_loftr_far   (default, configs[1])  FAR-LoFTR forward (ResNet-FPN -> 3x(self,cross) linear-attention layers ->
+                   dual-softmax coarse matching -> 5x5 fine level) -> RANSAC round -> FAR head (regress LoFTR layers ->
+                   EMM dual-softmax bilinear attention -> gated pose MLP) -> prior-guided RANSAC round -> FAR head again,
+                   32 pairs 640x480 per GPU, weak scaling.
+  vit8pt_b64       (configs[2])  ViTEss forward, batch 64, cached solver poses.  Weak scaling.
+  mapfree_6dreg    (configs[3])  RegressionModel.forward: upstream LoFTR (8 coarse layers, 6120 tokens) + RANSAC rounds +
+                   ResUNet + correlation-volume aggregator + TransformerEncoder + gated fusion, 16 pairs per GPU.
+  micro_4096x2048  (configs[4])  dual-softmax + mutual-NN matching on [P,2048,256] features and weighted 8-point +
+                   essential decomposition on [P,2048,2] correspondences, P = 4096 pairs in total: STRONG scaling
+                   (P / N pairs per GPU), the designated 1 -> 8 sweep.
+Random-init (seeded) weights; thr = 0 so random features still produce ~1.1k matches/pair.
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, library profiling OFF.  `e2e`: pinned host inputs,
+H2D on a side stream (double buffered), D2H of the result and (N > 1) the final all-gather inside the timed region.
+`roofline`: a separate instrumented pass (per-kernel CUDA events inside the library), top 3 kernels.
+`gpu_eager_baseline`: the reference's op sequence (oracle port, plain torch ops) on the same B200 in eager fp32 -- the
+bar SURVEY.md 8d names; `cpu_baseline`: the same port on the host cores.
 """
 import argparse
 import json
@@ -70,82 +80,509 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-# ---------------------------------------------------------------------------------------------- workload
-def build_inputs(pairs, seed):
-    from far_b200 import synth
-    img0, img1 = synth.synth_pair_images(pairs, seed=seed)
-    return img0, img1
+def _timed_loop(fn, seconds, max_iters=1000):
+    """(iterations, wall seconds) of fn() repeated for about `seconds` (CPU legs)."""
+    t0, n = time.perf_counter(), 0
+    while n < max_iters and (n == 0 or time.perf_counter() - t0 < seconds):
+        fn()
+        n += 1
+    return n, time.perf_counter() - t0
 
 
-def cfg_and_weights():
-    from far_b200 import synth
-    from far_b200.loftr import LoFTR, far_eval_cfg
-    cfg = far_eval_cfg(thr=0.0)
-    model = LoFTR(cfg)
-    sd = synth.synth_state_dict(model.state_dict(), 1234)
-    return cfg, model, sd
+def _gpu_time(fn, iters):
+    """Mean device ms of fn() (CUDA events on the current stream, one warm-up call)."""
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
 
 
-def flops_emm_call(B, N=4800, h=4, d=64):
-    """Algorithmic FLOPs of one far_emm_bilinear_attn call (both directions): S computed twice (LSE pass + recompute
-    pass), P V' once, V'^T T once (SURVEY.md 8d 'EMM bilinear attention')."""
-    dv = d + 6
-    per_dir = 2 * (2.0 * N * N * d) + 2.0 * N * N * dv + 2.0 * N * dv * dv
-    return 2 * B * h * per_dir
+# ======================================================================================================= workloads
+class Workload:
+    """One BASELINE config.  Subclasses fill: name, metric, scaling, units (pairs per rank per step), config dict,
+    setup(dev, rank, world), host_inputs() -> list of pinned CPU tensors, to_device(list) -> device inputs,
+    step(device inputs) -> result tensor(s) to read back, cpu_step() / eager_step() for the baselines."""
+    metric, unit, dtype, scaling = "image-pairs/sec @640x480", "pairs/s", "f32", "weak"
+
+    def result_tensors(self, out):
+        return out
+
+    def gather(self, out, world):
+        return None
 
 
-def cpu_oracle_step(sd, cfg, img0, img1, K):
-    """The reference's algorithm for the same workload on the host cores (oracle port), one pair at a time exactly
-    like the reference's B=1 evaluation."""
-    from oracle import far_oracle as O
-    n = img0.shape[0]
-    with torch.no_grad():
-        for b in range(n):
-            d = O.loftr_forward(sd, img0[b:b + 1], img1[b:b + 1], cfg)
-            R, t, E = O.pose_from_matches_8pt(d["mkpts0_f"], d["mkpts1_f"], d["mconf"], K, K)
-            rt = torch.cat([R, t[:, None]], 1)
-            M = int(d["b_ids"].shape[0])
-            for _ in range(cfg["fine_pred_steps"]):
-                lp, ilp = O.preprocess_helper(rt, M, M, 0, 0)
-                O.far_head_mp3d(O._sub(sd, "loftr_regress"), d["featmap0"], d["featmap1"], lp, ilp, cfg)
+# ------------------------------------------------------------------------------------------------ configs[1]
+class Mp3dLoftrFar(Workload):
+    name = "mp3d_loftr_far"
+
+    def __init__(self, args):
+        self.args = args
+        self.units = args.pairs if args.pairs else 32
+
+    def _cfg_weights(self):
+        from far_b200 import synth
+        from far_b200.loftr import LoFTR, far_eval_cfg
+        cfg = far_eval_cfg(thr=0.0)
+        model = LoFTR(cfg)
+        return cfg, model, synth.synth_state_dict(model.state_dict(), 1234)
+
+    def setup(self, dev, rank, world):
+        from far_b200 import synth
+        from far_b200.pipeline import FarPosePipeline
+        self.dev = dev
+        cfg, model, sd = self._cfg_weights()
+        cfg["regress"]["reuse_trunk"] = not self.args.no_trunk_reuse
+        model.load_state_dict(sd, strict=True)
+        self.model = model.to(dev).eval()
+        self.img = synth.synth_pair_images(self.units, seed=20240002 + rank)
+        K = synth.mp3d_intrinsics(self.units).to(dev)
+        self.pipe = FarPosePipeline(self.model, K, K, prior_ransac=not self.args.no_prior_ransac,
+                                    first_solver=self.args.first_solver)
+        self.nmatch = None
+
+    def host_inputs(self):
+        return [t.pin_memory() for t in self.img]
+
+    def step(self, inp):
+        out = self.pipe(inp[0], inp[1])
+        self.nmatch = out["num_matches"]
+        return out
+
+    def result_tensors(self, out):
+        return [out["pose"], out["num_matches"]]
+
+    def gather(self, out, world):
+        from far_b200.pipeline import gather_poses
+        poses, counts = gather_poses(out["pose"], out["num_matches"])
+        assert poses.shape[0] == self.units * world
+        return poses
+
+    def config(self, world):
+        a = self.args
+        return {"workload": self.name, "pairs_per_gpu": self.units, "global_pairs": self.units * world,
+                "image": "640x480 gray", "thr": 0.0, "coarse_layers": 3, "fine_pred_steps": 2,
+                "first_solver_call": "RANSAC round on the GPU, uniform sampling (2048 hypotheses/pair)"
+                if a.first_solver == "ransac" else "mconf-weighted 8-point + cheirality (SURVEY 8d config 2 literal)",
+                "second_solver_call": "prior-guided RANSAC round on the GPU (2048 hypotheses/pair)"
+                if not a.no_prior_ransac else "same as the first call",
+                "head_trunk": "evaluated once per forward and reused by the 2nd head invocation (identical outputs; "
+                              "--no-trunk-reuse re-evaluates it)" if not a.no_trunk_reuse else
+                              "re-evaluated by each of the 2 head invocations",
+                "matches_per_pair": float(self.nmatch.float().mean()) if self.nmatch is not None else None,
+                "parallelism": f"pairs sharded dp{world}",
+                "l2": "working set (inputs 79 MB + weights 204 MB + activations >> 126 MB L2): inputs larger than L2",
+                "backbone": "cuDNN conv with TF32 allowed (the reference's torch default); all other math fp32"}
+
+    # ---- baselines: the oracle port, one pair at a time exactly like the reference's B=1 evaluation
+    def _oracle_pairs(self, sd, cfg, img0, img1, K):
+        from oracle import far_oracle as O
+        n = img0.shape[0]
+        with torch.no_grad():
+            for b in range(n):
+                d = O.loftr_forward(sd, img0[b:b + 1], img1[b:b + 1], cfg)
                 R, t, E = O.pose_from_matches_8pt(d["mkpts0_f"], d["mkpts1_f"], d["mconf"], K, K)
-    return n
+                rt = torch.cat([R, t[:, None]], 1)
+                M = int(d["b_ids"].shape[0])
+                for _ in range(cfg["fine_pred_steps"]):
+                    lp, ilp = O.preprocess_helper(rt, M, M, 0, 0)
+                    O.far_head_mp3d(O._sub(sd, "loftr_regress"), d["featmap0"], d["featmap1"], lp, ilp, cfg)
+                    R, t, E = O.pose_from_matches_8pt(d["mkpts0_f"], d["mkpts1_f"], d["mconf"], K, K)
+        return n
+
+    def cpu_setup(self, pairs=1):
+        from far_b200 import synth
+        cfg, _, sd = self._cfg_weights()
+        i0, i1 = synth.synth_pair_images(pairs, seed=20240002)
+        K = synth.mp3d_intrinsics(1)[0]
+        return lambda: self._oracle_pairs(sd, cfg, i0, i1, K), pairs
+
+    def eager_setup(self, dev, pairs=4):
+        from far_b200 import synth
+        cfg, _, sd = self._cfg_weights()
+        sd = {k: v.to(dev) for k, v in sd.items()}
+        i0, i1 = synth.synth_pair_images(pairs, seed=20240002)
+        i0, i1, K = i0.to(dev), i1.to(dev), synth.mp3d_intrinsics(1)[0].to(dev)
+
+        def run():
+            with torch.device(dev):
+                self._oracle_pairs(sd, cfg, i0, i1, K)
+        return run, pairs
 
 
+# ------------------------------------------------------------------------------------------------ configs[2]
+class Vit8ptB64(Workload):
+    name = "vit8pt_b64"
+
+    def __init__(self, args):
+        self.args = args
+        self.units = args.pairs if args.pairs else 64
+
+    def _model(self):
+        import types
+        from far_b200 import synth
+        from far_b200.vit8pt import ViTEss
+        # interiornet-T normalisation (test_streetlearn_interiornet.py:179-180 layout: 9-D mean / std)
+        mean = torch.tensor([0.0, 0.0, 0.5, 0.9, 0.0, 0.0, 0.0, 0.9, 0.0])
+        std = torch.tensor([0.3, 0.2, 0.4, 0.1, 0.1, 0.2, 0.1, 0.1, 0.2])
+        a = types.SimpleNamespace(pool_size=60, fc_hidden_size=512, use_loftr_gating=True, use_normalized_6d=True,
+                                  fusion_transformer=True, transformer_depth=6, T_pose=torch.tensor([[0., 0., 1.]]))
+        m = ViTEss(a, mean, std)
+        return m, synth.synth_state_dict(m.state_dict(), 1234), mean, std
+
+    def _inputs(self, n, seed):
+        g = np.random.default_rng(seed)
+        img = torch.from_numpy(g.integers(0, 256, size=(n, 2, 3, 480, 640), dtype=np.uint8)).float()
+        intr = torch.tensor([[[128.0, 128.0, 128.0, 128.0]] * 2] * n)
+        ang = g.uniform(0, np.pi / 6, n)
+        lp = torch.eye(4, dtype=torch.float64)[None, :3].repeat(n, 1, 1)
+        lp[:, 0, 0] = lp[:, 1, 1] = torch.from_numpy(np.cos(ang))
+        lp[:, 0, 1], lp[:, 1, 0] = torch.from_numpy(-np.sin(ang)), torch.from_numpy(np.sin(ang))
+        t = g.standard_normal((n, 3))
+        lp[:, :, 3] = torch.from_numpy(t / np.linalg.norm(t, axis=1, keepdims=True))
+        nc = torch.from_numpy(g.integers(0, 1000, size=(n,)).astype(np.int64))
+        return img, intr, lp, nc
+
+    def setup(self, dev, rank, world):
+        self.dev = dev
+        m, sd, _, _ = self._model()
+        m.load_state_dict(sd, strict=True)
+        self.model = m.to(dev).eval().to(memory_format=torch.channels_last)
+        self.img, self.intr, lp, nc = self._inputs(self.units, 20240003 + rank)
+        self.lp, self.nc = lp.to(dev), nc.to(dev)
+
+    def host_inputs(self):
+        return [self.img.pin_memory()]
+
+    def step(self, inp):
+        with torch.no_grad():
+            t, rot, R, r6 = self.model(inp[0], self.intr.clone(), loftr_num_corr=self.nc, loftr_preds=self.lp)
+        return torch.cat([R.reshape(-1, 9), t], dim=1)
+
+    def result_tensors(self, out):
+        return [out]
+
+    def gather(self, out, world):
+        import torch.distributed as dist
+        buf = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(buf, out)
+        return torch.cat(buf)
+
+    def config(self, world):
+        return {"workload": self.name, "pairs_per_gpu": self.units, "global_pairs": self.units * world,
+                "image": "640x480 BGR 0-255 (resized to 224 by the model)", "transformer_depth": 6,
+                "solver_inputs": "cached: random rotation <= 30 deg + unit t, num_corr ~ U{0..1000} (SURVEY 8d)",
+                "parallelism": f"pairs sharded dp{world}", "l2": "inputs 472 MB per step: larger than L2",
+                "backbone": "resnet18 stem on cuDNN (TF32 allowed, torch default), everything after on the C ABI"}
+
+    def _oracle(self, m, sd, img, intr, lp, nc, mean, std):
+        from oracle import far_oracle as O
+        with torch.no_grad():
+            feats, intr2 = m.extract_features(img.clone(), intr.clone())
+            pos = O.emm_positional_encodings_vit(intr2)
+            O.vit_fusion_head(sd, feats, pos, lp, nc, mean.to(feats.device), std.to(feats.device))
+
+    def cpu_setup(self, pairs=8):
+        m, sd, mean, std = self._model()
+        m.load_state_dict(sd)
+        m = m.eval()
+        img, intr, lp, nc = self._inputs(pairs, 20240003)
+        return lambda: self._oracle(m, sd, img, intr, lp, nc, mean, std), pairs
+
+    def eager_setup(self, dev, pairs=64):
+        m, sd, mean, std = self._model()
+        m.load_state_dict(sd)
+        m = m.to(dev).eval()
+        sd = {k: v.to(dev) for k, v in sd.items()}
+        img, intr, lp, nc = self._inputs(pairs, 20240003)
+        img, lp, nc = img.to(dev), lp.to(dev), nc.to(dev)
+
+        def run():
+            with torch.device(dev):
+                self._oracle(m, sd, img, intr, lp, nc, mean, std)
+        return run, pairs
+
+
+# ------------------------------------------------------------------------------------------------ configs[3]
+class Mapfree6dreg(Workload):
+    name = "mapfree_6dreg"
+    metric = "image-pairs/sec @720x544 matcher + 360x270 regression"
+
+    def __init__(self, args):
+        self.args = args
+        self.units = args.pairs if args.pairs else 16
+
+    def _model(self):
+        from far_b200 import synth
+        from far_b200.mapfree import RegressionModel
+        m = RegressionModel(use_loftr_preds=True, use_vanilla_transformer=True, use_prior=True, inference=True)
+        m.matcher.config["match_coarse"]["thr"] = 0.0
+        m.matcher.coarse_matching.thr = 0.0
+        # temp_bug_fix True: with random-init weights the upstream default (False) gives a flat dual-softmax and ~20
+        # matches per pair; the fixed positional table gives ~1.2k, the load a trained matcher produces
+        m.matcher.config["coarse"]["temp_bug_fix"] = True
+        from far_b200.loftr.position_encoding import PositionEncodingSine
+        m.matcher.pos_encoding = PositionEncodingSine(256, temp_bug_fix=True)
+        return m, synth.synth_state_dict(m.state_dict(), 1234)
+
+    def setup(self, dev, rank, world):
+        from far_b200 import synth
+        self.dev = dev
+        m, sd = self._model()
+        m.load_state_dict(sd, strict=True)
+        self.model = m.to(dev).eval()
+        self.imgs = synth.synth_mapfree_images(self.units, 20240004 + rank)
+        self.K = synth.mapfree_intrinsics(self.units)
+        self.Kd = self.K.to(dev)
+        self.nmatch = None
+
+    def host_inputs(self):
+        return [t.pin_memory() for t in self.imgs]
+
+    def step(self, inp):
+        data = {"image0": inp[0], "image1": inp[1], "image0_reg": inp[2], "image1_reg": inp[3], "K_color0": self.K,
+                "K_color1": self.K}
+        R, t = self.model(data)
+        self.nmatch = data["mkpts0_f"].shape[0] / self.units
+        return torch.cat([R, t], dim=1)
+
+    def result_tensors(self, out):
+        return [out]
+
+    def gather(self, out, world):
+        import torch.distributed as dist
+        buf = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(buf, out)
+        return torch.cat(buf)
+
+    def config(self, world):
+        return {"workload": self.name, "pairs_per_gpu": self.units, "global_pairs": self.units * world,
+                "matcher": "upstream LoFTR, 4x(self,cross) coarse layers, 720x544 -> 6120 coarse tokens, thr 0, "
+                           "temp_bug_fix True (random-init weights give ~20 matches with the default False)",
+                "regression": "ResUNet(3-3-3 bottleneck) x2 at 360x270 -> correlation volume 6256^2 (tcgen05 flash kernel) "
+                              "-> DeepResBlock -> TransformerEncoder(6) -> gated fusion; use_prior: 2 solver rounds",
+                "matches_per_pair": self.nmatch, "parallelism": f"pairs sharded dp{world}",
+                "l2": "inputs 113 MB + activations >> 126 MB L2: inputs larger than L2",
+                "backbone": "cuDNN convs with TF32 allowed (torch default); matcher / aggregator / transformer / MLPs fp32"}
+
+    def _oracle(self, m, sd, cfg, imgs, K):
+        """Reference op sequence: per-sample upstream LoFTR + solver, then the image branch (model.py:235-308)."""
+        from oracle import far_oracle as O
+        i0, i1, r0, r1 = imgs
+        B = i0.shape[0]
+        msd = O._sub(sd, "matcher")
+        with torch.no_grad():
+            rts, inl = [], []
+            for loop in range(2):
+                for b in range(B):
+                    d = O.loftr_forward(msd, i0[b:b + 1], i1[b:b + 1], cfg)
+                    R, t, E = O.pose_from_matches_8pt(d["mkpts0_f"], d["mkpts1_f"], d["mconf"], K[b], K[b])
+                    if loop == 1:
+                        rts.append(torch.cat([R, t[:, None]], 1)[None])
+                        inl.append(float(d["mkpts0_f"].shape[0]))
+                v0, v1 = m.encoder(r0), m.encoder(r1)
+                agg = O.mapfree_correlation_aggregator(v0.contiguous(), v1.contiguous())
+                _, _, x3 = m.head(agg, None)
+                tr = O.torch_transformer_encoder(O._sub(sd, "transformer"), x3.reshape(B, 256, 108).permute(2, 0, 1))
+            feats = tr.permute(1, 2, 0).reshape(B, -1)
+            inl3 = torch.tensor(inl, device=feats.device)[:, None].repeat(1, 3)
+            O.mapfree_regression_mlp(sd, feats, torch.cat(rts), inl3)
+
+    def _eager_parts(self, dev, pairs):
+        from far_b200 import synth
+        from far_b200.loftr import upstream_loftr_cfg
+        m, sd = self._model()
+        m.load_state_dict(sd)
+        m = m.to(dev).train(False)
+        for mod in m.modules():       # plain torch path of the conv blocks (no folded / fused fast path)
+            mod.force_eager = True
+        cfg = upstream_loftr_cfg()
+        cfg["match_coarse"]["thr"] = 0.0
+        cfg["coarse"]["temp_bug_fix"] = True
+        imgs = [t.to(dev) for t in synth.synth_mapfree_images(pairs, 20240004)]
+        K = synth.mapfree_intrinsics(pairs).to(dev)
+        return m, {k: v.to(dev) for k, v in sd.items()}, cfg, imgs, K
+
+    def cpu_setup(self, pairs=1):
+        m, sd, cfg, imgs, K = self._eager_parts(torch.device("cpu"), pairs)
+        return lambda: self._oracle(m, sd, cfg, imgs, K), pairs
+
+    def eager_setup(self, dev, pairs=2):
+        m, sd, cfg, imgs, K = self._eager_parts(dev, pairs)
+
+        def run():
+            with torch.device(dev):
+                self._oracle(m, sd, cfg, imgs, K)
+        return run, pairs
+
+
+# ------------------------------------------------------------------------------------------------ configs[4]
+class Micro4096x2048(Workload):
+    name = "micro_4096x2048"
+    metric, scaling = "pairs/sec (dual-softmax match @2048 tokens + 8-point @2048 correspondences)", "strong"
+    P_TOTAL, NTOK, NCORR, CHUNK = 4096, 2048, 2048, 128
+
+    def __init__(self, args):
+        self.args = args
+        self.units = None
+
+    def setup(self, dev, rank, world):
+        from far_b200 import synth
+        from far_b200.pipeline import shard_pairs
+        self.dev = dev
+        total = self.args.pairs if self.args.pairs else self.P_TOTAL
+        a, b = shard_pairs(total, world, rank)
+        self.units = b - a
+        self.total = total
+        g = torch.Generator(device=dev).manual_seed(20240005 + rank)
+        # (ii) features ~ N(0,1) scaled so the dual-softmax is peaked like post-transformer features
+        self.f0 = torch.randn(self.units, self.NTOK, 256, device=dev, generator=g) * 2.5
+        self.f1 = torch.randn(self.units, self.NTOK, 256, device=dev, generator=g) * 2.5
+        # (i) two-view geometry, 20 % outliers, w ~ U(0,1)   (SURVEY.md 8d config 5)
+        nb = min(self.units, 256)
+        p1, p2, w, _, _ = synth.two_view_geometry(nb, self.NCORR, seed=5 + rank)
+        rep = (self.units + nb - 1) // nb
+        self.p1 = p1.repeat(rep, 1, 1)[:self.units].contiguous().to(dev)
+        self.p2 = p2.repeat(rep, 1, 1)[:self.units].contiguous().to(dev)
+        self.w = w.repeat(rep, 1)[:self.units].contiguous().to(dev)
+        self.nmatch = 0.0
+
+    def host_inputs(self):
+        # one pinned chunk per operand, re-sent for every chunk of the step (same bytes over PCIe, synthetic data)
+        c = min(self.CHUNK, self.units)
+        return [self.f0[:c].cpu().pin_memory(), self.f1[:c].cpu().pin_memory(), self.p1.cpu().pin_memory(),
+                self.p2.cpu().pin_memory(), self.w.cpu().pin_memory()]
+
+    def _run(self, f0, f1, p1, p2, w, chunk_src=None):
+        from far_b200 import ops
+        M = 0
+        outs = []
+        for c0 in range(0, self.units, self.CHUNK):
+            c1 = min(c0 + self.CHUNK, self.units)
+            if chunk_src is not None:      # e2e: every chunk crosses PCIe
+                a0 = chunk_src[0][:c1 - c0].to(self.dev, non_blocking=True)
+                a1 = chunk_src[1][:c1 - c0].to(self.dev, non_blocking=True)
+            else:
+                a0, a1 = f0[c0:c1], f1[c0:c1]
+            d = ops.dual_softmax_match(a0, a1, (32, 64), (32, 64), 0.0, 0, 0.1, 8.0, 8.0)
+            M += d["b_ids"].shape[0]
+            outs.append(d["mconf"].sum().reshape(1))
+        F = ops.eight_point(p1, p2, w)
+        R1, R2, t = ops.essential_decompose(F)
+        self.nmatch = M / self.units
+        return torch.cat([F.reshape(-1, 9), R1.reshape(-1, 9), t.reshape(-1, 3)], 1), torch.cat(outs)
+
+    def to_device(self, host):
+        return [host, host[2].to(self.dev, non_blocking=True), host[3].to(self.dev, non_blocking=True),
+                host[4].to(self.dev, non_blocking=True)]
+
+    def step(self, inp):
+        if isinstance(inp, dict):          # resident
+            return self._run(self.f0, self.f1, self.p1, self.p2, self.w)
+        host, p1, p2, w = inp
+        return self._run(None, None, p1, p2, w, chunk_src=host)
+
+    def result_tensors(self, out):
+        return [out[0], out[1]]
+
+    def gather(self, out, world):
+        import torch.distributed as dist
+        sizes = [torch.zeros(1, dtype=torch.int64, device=self.dev) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([out[0].shape[0]], device=self.dev))
+        mx = int(max(s.item() for s in sizes))
+        pad = torch.zeros(mx, out[0].shape[1], device=self.dev)
+        pad[:out[0].shape[0]] = out[0]
+        buf = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(buf, pad)
+        return torch.cat([b[:int(s.item())] for b, s in zip(buf, sizes)])
+
+    def config(self, world):
+        return {"workload": self.name, "global_pairs": self.total, "pairs_per_gpu": self.units,
+                "tokens": self.NTOK, "correspondences": self.NCORR, "chunk_pairs": self.CHUNK,
+                "matcher": "far_dual_softmax_match_* from features (T 0.1, thr 0, border 0, grid 32x64); the "
+                           "[P,2048,2048] score / confidence matrices are never written",
+                "solver": "far_eight_point (weights ~U(0,1), 20% outliers) + far_essential_decompose",
+                "matches_per_pair": self.nmatch, "parallelism": f"P/G pairs per GPU, dp{world}",
+                "l2": f"features {self.units * 4.2e-3:.1f} GB per rank: larger than L2",
+                "algorithmic_bytes_per_pair": {"match_fused_from_features": 2 * self.NTOK * 256 * 4,
+                                               "eight_point": 20 * self.NCORR + 144}}
+
+    def _oracle(self, f0, f1, p1, p2, w, chunk):
+        from oracle import far_oracle as O
+        with torch.no_grad():
+            for c0 in range(0, f0.shape[0], chunk):
+                conf = O.dual_softmax_conf(f0[c0:c0 + chunk], f1[c0:c0 + chunk], 0.1)
+                O.coarse_match_from_conf(conf, (32, 64), (32, 64), 0.0, 0, 8.0)
+                del conf
+            for c0 in range(0, p1.shape[0], 64):
+                F = O.run_8point(p1[c0:c0 + 64], p2[c0:c0 + 64], w[c0:c0 + 64], dense_diag=True)
+                O.decompose_essential_matrix(F)
+
+    def cpu_setup(self, pairs=4):
+        g = torch.Generator().manual_seed(1)
+        from far_b200 import synth
+        f0 = torch.randn(pairs, self.NTOK, 256, generator=g) * 2.5
+        f1 = torch.randn(pairs, self.NTOK, 256, generator=g) * 2.5
+        p1, p2, w, _, _ = synth.two_view_geometry(pairs, self.NCORR, seed=5)
+        return lambda: self._oracle(f0, f1, p1, p2, w, 4), pairs
+
+    def eager_setup(self, dev, pairs=64):
+        pairs = min(pairs, self.units)
+        f0, f1, p1, p2, w = self.f0[:pairs], self.f1[:pairs], self.p1[:pairs], self.p2[:pairs], self.w[:pairs]
+
+        def run():
+            with torch.device(dev):
+                self._oracle(f0, f1, p1, p2, w, 16)
+        return run, pairs
+
+
+WORKLOADS = {w.name: w for w in (Mp3dLoftrFar, Vit8ptB64, Mapfree6dreg, Micro4096x2048)}
+
+
+# ======================================================================================================= reference arm
 def run_reference(args, rank, world):
-    """--impl reference: rank 0 alone runs; each step = a bounded sample (1 pair) of the same workload."""
+    """--impl reference: rank 0 alone runs; each step = a bounded sample of the same workload on the host cores."""
     if rank != 0:
         return
-    from far_b200 import synth
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg, model, sd = cfg_and_weights()
-    del model
-    sample_pairs = 1
-    img0, img1 = build_inputs(sample_pairs, 20240002)
-    K = synth.mp3d_intrinsics(1)[0]
+    wl = WORKLOADS[args.workload](args)
+    fn, sample_pairs = wl.cpu_setup()
     for _ in range(args.warmup):
-        cpu_oracle_step(sd, cfg, img0, img1, K)
+        fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_oracle_step(sd, cfg, img0, img1, K)
+        fn()
     dt = time.perf_counter() - t0
     v = sample_pairs * args.steps / dt
     cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": "image-pairs/sec @640x480", "value": v, "unit": "pairs/s",
+    line = {"impl": "reference", "metric": wl.metric, "value": v, "unit": wl.unit,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "mp3d_loftr_far", "pairs_per_step": sample_pairs, "thr": 0.0,
+            "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "pairs_per_step": sample_pairs, "thr": 0.0,
                        "note": "CPU restatement of the reference (oracle port), torch CPU fp32, all host threads"},
-            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": v, "unit": wl.unit, "cores": cores, "kind": "port",
                              "sample": f"{sample_pairs} pair(s)/step x {args.steps} steps of the same workload"},
-            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ======================================================================================================= our arm
+ALGO_NOTE = {
+    "tc_gemm_kernel": "3xTF32 error-compensated fp32 GEMM: 3 tensor-core MMAs per algorithmic FMA, so frac <= 1/3 of the "
+                      "tf32 pipe (= 1/6 of the bf16 peak used as denominator)",
+    "tc_emm_pv_kernel": "3xTF32 S = QK^T and P V' (A operand from TMEM): same 1/6 ceiling; algorithmic FLOPs of SURVEY 8d",
+    "tc_score_kernel": "3xTF32 score tiles + one MUFU.EX2 per exponential (MUFU co-bound); includes tc_lse64",
+    "tc_corrvol_kernel": "3xTF32; two sweeps of S (row maximum, recompute) + P V' per query tile",
+}
 
 
 def run_far(args, rank, world, local_rank):
     import torch.distributed as dist
-    from far_b200 import synth, ops, _lib
-    from far_b200.pipeline import FarPosePipeline, gather_poses
+    from far_b200 import ops, _lib
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     # the reference's own GPU default: TF32 allowed inside cuDNN convolutions (torch default), matmuls IEEE fp32;
@@ -153,147 +590,179 @@ def run_far(args, rank, world, local_rank):
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
-    cfg, model, sd = cfg_and_weights()
-    cfg["regress"]["reuse_trunk"] = not args.no_trunk_reuse
-    model.load_state_dict(sd, strict=True)
-    model = model.to(dev).eval()
-    pairs = args.pairs
-    img0_h, img1_h = build_inputs(pairs, 20240002 + rank)
-    img0_h, img1_h = img0_h.pin_memory(), img1_h.pin_memory()
-    K = synth.mp3d_intrinsics(pairs).to(dev)
-    pipe = FarPosePipeline(model, K, K, prior_ransac=not args.no_prior_ransac)
+    wl = WORKLOADS[args.workload](args)
+    wl.setup(dev, rank, world)
     lib = _lib.load()
+    host = wl.host_inputs()
+    to_device = getattr(wl, "to_device", lambda hs: [h.to(dev, non_blocking=True) for h in hs])
+    resident = {"resident": True} if isinstance(wl, Micro4096x2048) else [h.to(dev) for h in host]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident(i0, i1):
-        return pipe(i0, i1)
-
-    def step_e2e():
-        i0 = img0_h.to(dev, non_blocking=True)
-        i1 = img1_h.to(dev, non_blocking=True)
-        out = pipe(i0, i1)
-        return out["pose"].cpu(), out["num_matches"].cpu()  # D2H read of the step's result
-
-    img0_d, img1_d = img0_h.to(dev), img1_h.to(dev)
     for _ in range(args.warmup):
-        out = step_resident(img0_d, img1_d)
+        out = wl.step(resident)
     barrier()
 
-    # ---------------- timed region 1: inputs resident in HBM (value) ----------------
+    # ---------------- timed region 1: inputs resident in HBM, no instrumentation (value) ----------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ops.timer = ops.OpTimer()
-    _lib.profile_enable(True)  # per-kernel CUDA-event pairs inside the library (far_profile_*, include/far_sm100.h)
     launches0 = lib.far_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        out = step_resident(img0_d, img1_d)
+        out = wl.step(resident)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.far_launch_count() - launches0
-    op_times = ops.timer.summary()
-    ops.timer = None
-    kern = _lib.profile_read()
-    _lib.profile_enable(False)
-    nmatch = int(out["num_matches"].sum().item())
 
     # ---------------- timed region 2: end to end through the public API with host buffers ----------------
-    step_e2e()
+    # H2D of step s+1 is issued on a side stream while step s computes (two device input slots); every step ends with
+    # the D2H read of its result, and with N > 1 the path's one collective (final all-gather) is inside the region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots, ready, done = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(slot, first=False):
+        if not first:
+            copy_stream.wait_event(done[slot])
+        with torch.cuda.stream(copy_stream):
+            slots[slot] = to_device(host)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(steps):
+        d2h = 0
+        prefetch(0, first=True)
+        for s in range(steps):
+            cur = s & 1
+            torch.cuda.current_stream().wait_event(ready[cur])
+            if s + 1 < steps:
+                prefetch(cur ^ 1, first=(s == 0))
+            o = wl.step(slots[cur])
+            done[cur].record()
+            if world > 1:
+                g = wl.gather(o, world)
+                res = [g.cpu()] if rank == 0 and g is not None else [t.cpu() for t in wl.result_tensors(o)]
+            else:
+                res = [t.cpu() for t in wl.result_tensors(o)]   # D2H read of the step's result (blocking)
+            d2h = sum(t.numel() * t.element_size() for t in res)
+        return d2h
+
+    e2e_loop(2)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(args.steps):
-        pose_h, cnt_h = step_e2e()
+    d2h_bytes = e2e_loop(args.steps)
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     sampler.stop_flag = True
+    h2d_bytes = sum(h.numel() * h.element_size() for h in host)
+    if isinstance(wl, Micro4096x2048):   # the feature chunk crosses PCIe once per chunk of the step
+        nchunks = (wl.units + wl.CHUNK - 1) // wl.CHUNK
+        h2d_bytes = (host[0].numel() + host[1].numel()) * 4 * nchunks + sum(h.numel() * 4 for h in host[2:])
 
-    if world > 1:  # max over ranks + the path's one collective (final pose gather)
-        tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = tt.tolist()
-        poses, counts = gather_poses(out["pose"], out["num_matches"])
-        assert poses.shape[0] == pairs * world
+    # ---------------- instrumented pass (outside the timed regions): per-kernel events -> roofline ----------------
+    ops.timer = ops.OpTimer()
+    _lib.profile_enable(True)
+    psteps = min(args.steps, 3)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(psteps):
+        out = wl.step(resident)
+    p1.record()
+    torch.cuda.synchronize()
+    ms_prof = p0.elapsed_time(p1)
+    op_times = ops.timer.summary()
+    ops.timer = None
+    kern = _lib.profile_read()
+    _lib.profile_enable(False)
+
+    per_rank = [ms, ms_e2e]
+    if world > 1:  # max over ranks; per-rank spread (ragged M per pair makes per-GPU work uneven)
+        mine = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu()
+        ms, ms_e2e = float(allr[:, 0].max()), float(allr[:, 1].max())
+        per_rank = allr
     if rank != 0:
         return
 
     hbm, tf, tf_sus, which = load_peaks()
-    total_pairs = pairs * world * args.steps
-    value = total_pairs / (ms / 1e3)
-    e2e = total_pairs / (ms_e2e / 1e3)
-    # dominant kernel for the roofline entry: the kernel class with the largest share of the step, timed live by the
-    # library's own CUDA events around each of its launches on the launching stream (not the C-ABI call around it)
-    top = sorted(op_times.items(), key=lambda kv: -kv[1][1])
-    share = {k: round(v[1] / ms, 4) for k, v in top}
-    kshare = {k: round(v["ms"] / ms, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}
-    roof = None
+    total_units = (wl.total if wl.scaling == "strong" else wl.units * world) * args.steps
+    value = total_units / (ms / 1e3)
+    e2e = total_units / (ms_e2e / 1e3)
+    share = {k: round(v[1] / ms_prof, 4) for k, v in sorted(op_times.items(), key=lambda kv: -kv[1][1])}
+    kshare = {k: round(v["ms"] / ms_prof, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}
     traffic_db = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         traffic_db = json.load(open(tpath))
-    if kern:
-        name, k = max(kern.items(), key=lambda kv: kv[1]["ms"])
+    roofs = []
+    for name, k in sorted(kern.items(), key=lambda kv: -kv[1]["ms"]):
+        if len(roofs) == 3 or k["launches"] == 0 or (k["flops"] == 0 and k["bytes"] == 0):
+            continue
         per_launch_s = k["ms"] / k["launches"] / 1e3
         tensor_bound = name.startswith("tc_")
         if tensor_bound:
-            achieved = k["flops"] / k["launches"] / per_launch_s / 1e12
-            peak, unit, src = tf_sus, "TFLOP/s", "bf16_tflops_sustained"
+            achieved, peak, unit, src = k["flops"] / k["launches"] / per_launch_s / 1e12, tf_sus, "TFLOP/s", "bf16_tflops_sustained"
         else:
-            achieved = k["bytes"] / k["launches"] / per_launch_s / 1e9
-            peak, unit, src = hbm, "GB/s", "hbm_gbs"
+            achieved, peak, unit, src = k["bytes"] / k["launches"] / per_launch_s / 1e9, hbm, "GB/s", "hbm_gbs"
         tr = traffic_db.get(name)
-        roof = {"kernel": name, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
-                "unit": unit, "frac": achieved / peak,
-                "peak_source": f"{src} of {which} MEASURED_PEAKS.json (kernel timed inside a long step)",
-                "us_per_launch": per_launch_s * 1e6, "launches_per_step": k["launches"] / args.steps,
-                "algorithmic_flops_per_launch": k["flops"] / k["launches"],
-                "algorithmic_bytes_per_launch": k["bytes"] / k["launches"],
-                "traffic": tr["dram_bytes_per_launch"] if tr else None,
-                "traffic_source": tr["source"] if tr else None,
-                "share_of_step": kshare.get(name),
-                "frac_of_3xtf32_ceiling": (achieved / (peak / 6.0)) if tensor_bound else None,
-                "note": "3xTF32 error-compensated fp32 GEMM: 3 tensor-core MMAs per algorithmic FMA, so frac <= 1/3 of "
-                        "the tf32 pipe (= 1/6 of the bf16 peak used as denominator); traffic = mean DRAM bytes per "
-                        "launch over one steady-state step (profiles/ncu_traffic.json)" if tensor_bound else None}
-    line = {"metric": "image-pairs/sec @640x480", "value": value, "unit": "pairs/s", "n_gpus": world,
+        roofs.append({"kernel": name, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
+                      "unit": unit, "frac": achieved / peak,
+                      "peak_source": f"{src} of {which} MEASURED_PEAKS.json (kernel timed inside a long step)",
+                      "us_per_launch": per_launch_s * 1e6, "launches_per_step": k["launches"] / psteps,
+                      "algorithmic_flops_per_launch": k["flops"] / k["launches"],
+                      "algorithmic_bytes_per_launch": k["bytes"] / k["launches"],
+                      "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                      "traffic_source": tr["source"] if tr else None, "share_of_step": kshare.get(name),
+                      "frac_of_3xtf32_ceiling": (achieved / (peak / 6.0)) if tensor_bound else None,
+                      "note": ALGO_NOTE.get(name)})
+    line = {"metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "mp3d_loftr_far", "pairs_per_gpu": pairs, "global_pairs": pairs * world,
-                       "image": "640x480 gray", "thr": 0.0, "coarse_layers": 3, "fine_pred_steps": 2,
-                       "second_solver_call": "prior-guided RANSAC round on the GPU (2048 hypotheses/pair)"
-                       if not args.no_prior_ransac else "weighted 8-point + cheirality (as the first call)",
-                       "head_trunk": "evaluated once per forward and reused by the 2nd head invocation (identical "
-                                     "outputs; --no-trunk-reuse re-evaluates it)" if not args.no_trunk_reuse else
-                                     "re-evaluated by each of the 2 head invocations",
-                       "matches_per_pair": nmatch / pairs, "parallelism": f"pairs sharded dp{world}",
-                       "l2": "working set (inputs 79 MB + weights 204 MB + activations >> 126 MB L2): inputs larger than L2",
-                       "backbone": "cuDNN conv with TF32 allowed (the reference's torch default); all other math fp32"},
-            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * img0_h.numel() * 4 * world),
-                    "d2h_bytes_per_step": int((pose_h.numel() * 4 + cnt_h.numel() * 8) * world),
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "op_share_of_step": share, "kernel_share_of_step": kshare, "clocks": sampler.summary(), "roofline": roof}
+            "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+            "config": wl.config(world),
+            "e2e": {"value": e2e, "unit": wl.unit, "h2d_bytes_per_step": int(h2d_bytes * world),
+                    "d2h_bytes_per_step": int(d2h_bytes * (1 if world > 1 else 1)), "ms_per_step": ms_e2e / args.steps,
+                    "includes": "H2D of the step's inputs (side stream, double buffered), D2H of the result"
+                                + (", final all-gather over NCCL" if world > 1 else "")},
+            "gpu_launches": int(launches), "timing": "value/e2e timed with library profiling OFF; roofline and the share "
+            "tables come from a separate instrumented pass of %d step(s)" % psteps,
+            "op_share_of_step": share, "kernel_share_of_step": kshare, "clocks": sampler.summary(),
+            "roofline": roofs[0] if roofs else None, "roofline_top3": roofs}
+    if world > 1:
+        line["per_rank_ms_per_step"] = {
+            "value": {"min": float(per_rank[:, 0].min()) / args.steps, "median": float(per_rank[:, 0].median()) / args.steps,
+                      "max": float(per_rank[:, 0].max()) / args.steps},
+            "e2e": {"min": float(per_rank[:, 1].min()) / args.steps, "median": float(per_rank[:, 1].median()) / args.steps,
+                    "max": float(per_rank[:, 1].max()) / args.steps}}
+    if world == 1 and not args.no_gpu_eager_baseline:
+        try:
+            fn, n = wl.eager_setup(dev)
+            torch.backends.cudnn.allow_tf32 = True       # the reference's torch defaults on a GPU
+            torch.backends.cuda.matmul.allow_tf32 = False
+            t_ms = _gpu_time(fn, 2)
+            line["gpu_eager_baseline"] = {
+                "value": n / (t_ms / 1e3), "unit": wl.unit, "ms_per_sample": t_ms, "sample": f"{n} pair(s) of the same "
+                "workload", "what": "the reference's op sequence (oracle port: plain torch ops, eager, fp32, cuDNN TF32 as "
+                "torch defaults) on this same GPU, CUDA-event timed; B=1 python loops kept where the reference has them"}
+            torch.cuda.empty_cache()
+        except Exception as ex:  # a baseline must never take the bench line down
+            line["gpu_eager_baseline"] = {"error": repr(ex)[:300]}
     if world == 1 and not args.no_cpu_baseline:
-        cfg2, _, sd2 = cfg_and_weights()
         torch.set_num_threads(os.cpu_count() or 1)
-        i0, i1 = build_inputs(1, 20240002)
-        Kc = synth.mp3d_intrinsics(1)[0]
-        cpu_oracle_step(sd2, cfg2, i0, i1, Kc)  # warm
-        t0 = time.perf_counter()
-        n = 0
-        while time.perf_counter() - t0 < 12.0:
-            n += cpu_oracle_step(sd2, cfg2, i0, i1, Kc)
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": n / dt, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{n} pair(s) of the same workload, one at a time (reference is batch-1), {dt:.1f} s"}
+        fn, n = wl.cpu_setup()
+        fn()  # warm
+        it, dt = _timed_loop(fn, 12.0)
+        line["cpu_baseline"] = {"value": n * it / dt, "unit": wl.unit, "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{n * it} pair(s) of the same workload, {n} at a time, {dt:.1f} s"}
     print(json.dumps(line), flush=True)
 
 
@@ -303,11 +772,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="far", choices=["far", "reference"])
-    ap.add_argument("--pairs", type=int, default=32, help="pairs per GPU per step (BASELINE configs[1]: 32)")
+    ap.add_argument("--workload", default="mp3d_loftr_far", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: the BASELINE config's: 32 / 64 "
+                    "/ 16; micro: TOTAL pairs, default 4096, strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
+    ap.add_argument("--first-solver", default="ransac", choices=["ransac", "weighted_8pt"],
+                    help="mp3d_loftr_far: first solver call = GPU RANSAC round (default; counters are inlier counts) or "
+                         "the single mconf-weighted 8-point fit")
     ap.add_argument("--no-prior-ransac", action="store_true",
-                    help="re-run the weighted 8-point between the two head invocations instead of the batched GPU "
-                         "prior-guided RANSAC round of the FAR recipe (far_b200/ransac.py, 2048 hypotheses per pair)")
+                    help="mp3d_loftr_far: re-run the first solver between the two head invocations instead of the "
+                         "prior-guided RANSAC round (far_b200/ransac.py, 2048 hypotheses per pair)")
     ap.add_argument("--no-trunk-reuse", action="store_true",
                     help="re-evaluate the FAR head trunk in both head invocations, literally as the reference does")
     args = ap.parse_args()

@@ -38,6 +38,7 @@ _SIGS = {
     "far_layernorm_pre": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
     "far_upsample2x_add_nhwc": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "far_scale_shift_act_nhwc": (c_int, [_P, _P, _P, c_longlong, c_int, c_float, _P]),
+    "far_scale_shift_act_nhwc_out": (c_int, [_P, _P, _P, _P, c_longlong, c_int, c_float, _P]),
     "far_stem_conv_workspace_bytes": (c_size_t, [c_int]),
     "far_stem_conv7x7s2_relu_nhwc": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "far_pos_encode_flatten": (c_int, [_P, c_longlong, c_longlong, c_longlong, c_longlong, _P, _P, c_int, c_int, c_int,
@@ -73,6 +74,9 @@ _SIGS = {
     "far_emm_bilinear_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "far_emm_bilinear_attn": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, c_int, _P,
                                       c_size_t, _P]),
+    "far_corr_volume_warp_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "far_corr_volume_warp": (c_int, [_P, _P, c_longlong, c_longlong, c_longlong, _P, c_int, c_int, c_int, _P, _P,
+                                     c_size_t, _P]),
     "far_softmax_attention_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "far_softmax_attention": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, _P, _P, c_size_t, _P]),
     "far_pose_blend_mp3d": (c_int, [_P, _P, c_int, _P, _P, _P, c_int, _P, c_int, _P]),

@@ -34,7 +34,7 @@ namespace far {
 enum ProfId {
   PROF_TC_GEMM = 0, PROF_TC_SCORE, PROF_TC_EMM_PV, PROF_LA_REDUCE, PROF_LA_APPLY, PROF_LA_SMALL, PROF_LAYERNORM,
   PROF_LINEAR_SIMT, PROF_FINE_GATHER, PROF_FINE_MATCH, PROF_SPLIT, PROF_EMM_SIMT, PROF_SOLVER, PROF_FPN, PROF_ENC_FUSED,
-  PROF_NUM_IDS
+  PROF_TC_CORRVOL, PROF_EIGHTPT, PROF_NUM_IDS
 };
 extern bool g_prof_on;
 void prof_begin(int id, double flops, double bytes, cudaStream_t st);

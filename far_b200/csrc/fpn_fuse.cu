@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) upsample2x_add_nhwc_kernel(const float4* 
 }
 
 // In place: x[p, c] = act(x[p, c] * scale[c] + shift[c]); act: ReLU or LeakyReLU(slope).  C % 4 == 0.
-__global__ void __launch_bounds__(256) scale_shift_act_nhwc_kernel(float4* __restrict__ x,
+__global__ void __launch_bounds__(256) scale_shift_act_nhwc_kernel(const float4* x, float4* y,
                                                                     const float4* __restrict__ scale,
                                                                     const float4* __restrict__ shift, long long total,
                                                                     int C4, float slope) {
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) scale_shift_act_nhwc_kernel(float4* __res
     v.y = v.y > 0.f ? v.y : v.y * slope;
     v.z = v.z > 0.f ? v.z : v.z * slope;
     v.w = v.w > 0.f ? v.w : v.w * slope;
-    x[idx] = v;
+    y[idx] = v;
   }
 }
 
@@ -184,8 +184,26 @@ extern "C" int far_scale_shift_act_nhwc(float* x, const float* scale, const floa
   const long long cap = (long long)kNumSMs * 32;
   if (blocks > cap) blocks = cap;
   scale_shift_act_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(scale), reinterpret_cast<const float4*>(shift),
-      total, C / 4, negative_slope);
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(scale),
+      reinterpret_cast<const float4*>(shift), total, C / 4, negative_slope);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+extern "C" int far_scale_shift_act_nhwc_out(const float* x, float* y, const float* scale, const float* shift,
+                                            long long pixels, int C, float negative_slope, void* stream) {
+  if (pixels <= 0 || C <= 0) return FAR_OK;
+  if (x == nullptr || y == nullptr || shift == nullptr || (C & 3) != 0) return FAR_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(scale) |
+       reinterpret_cast<uintptr_t>(shift)) & 15u)
+    return FAR_ERR_ARG;
+  const long long total = pixels * (C / 4);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  scale_shift_act_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(scale),
+      reinterpret_cast<const float4*>(shift), total, C / 4, negative_slope);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }

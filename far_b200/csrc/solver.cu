@@ -430,7 +430,8 @@ __global__ void __launch_bounds__(256) ransac_score_kernel(RaggedPts pts, int P,
     float r1[9], r2[9], tt[3];
     essential_decompose(E, r1, r2, tt);
     const float* pr = prior_rt + (size_t)pair * 12;
-    const float tn = rsqrtf(pr[3] * pr[3] + pr[7] * pr[7] + pr[11] * pr[11]);   // setup_prior: unit translation (:180)
+    // setup_prior: unit translation (:180); a zero prior translation stays zero instead of poisoning every score with NaN
+    const float tn = 1.f / fmaxf(sqrtf(pr[3] * pr[3] + pr[7] * pr[7] + pr[11] * pr[11]), 1e-12f);
     // The sign of T = U[:, 2] is an artefact of the SVD routine (E fixes t only up to sign).  The reference scores
     // whichever sign LAPACK returns (ransac.py:215-224); here both signs are scored and the better one counts, which
     // equals the reference's value whenever LAPACK's sign is the better one and is never worse.
@@ -733,6 +734,8 @@ extern "C" int far_eight_point(const float* pts1, const float* pts2, const float
   cudaStream_t st = (cudaStream_t)stream;
   double* rec = reinterpret_cast<double*>(workspace);
   DensePts pts{pts1, pts2, weights, counts, N};
+  // algorithmic bytes: 20 N in (two point sets + weight) + 36 out per pair; ~120 N FLOP
+  ProfScope prof(PROF_EIGHTPT, 120.0 * N * (double)P, ((weights ? 20.0 : 16.0) * N + 36.0) * (double)P, st);
   eightpt_accumulate_kernel<DensePts><<<ceil_div(P, 4), 128, 0, st>>>(pts, P, rec);
   FAR_CHECK_LAUNCH();
   eightpt_solve_kernel<<<ceil_div(P, 64), 64, 0, st>>>(rec, P, F);

@@ -174,6 +174,22 @@ def scale_shift_act_(x, scale, shift, negative_slope):
     return x
 
 
+def scale_shift_act(x, scale, shift, negative_slope):
+    """Out-of-place leaky_relu(x*scale[c] + shift[c]) on a channels_last [N,C,H,W] map: the pre-activation
+    relu(bn(x)) of the map-free PreAct blocks (encoder/preact.py:35,68), x stays alive as the identity shortcut."""
+    lib = L.load()
+    n, c, h, w = x.shape
+    x_ = x.permute(0, 2, 3, 1)
+    if not x_.is_contiguous() or x.dtype != torch.float32:
+        raise L.FarError("scale_shift_act needs a dense fp32 channels_last tensor")
+    y = torch.empty_like(x)
+    with _timed("far_scale_shift_act_nhwc"):
+        check(lib.far_scale_shift_act_nhwc_out(ptr(x_), ptr(y), ptr(f32c(scale)) if scale is not None else None,
+                                               ptr(f32c(shift)), n * h * w, c, float(negative_slope), stream()),
+              "far_scale_shift_act_nhwc_out")
+    return y
+
+
 def linear_attention(q, k, v, eps=1e-6, feature_map_applied=False):
     """LinearAttention.forward (linear_attention.py:20-52).  q [N,L,H,D]; k,v [N,S,H,D] -> [N,L,H,D]."""
     lib = L.load()
@@ -423,6 +439,45 @@ def emm_bilinear_attn(qkv1, qkv2, pos, num_heads, scale, engine=L.ENGINE_AUTO):
         check(lib.far_emm_bilinear_attn(ptr(q1), ptr(q2), ptr(p_), p_.shape[0], B, N, num_heads, d, float(scale), ptr(F1),
                                       ptr(F2), engine, ptr(ws), ws.numel(), stream()), "far_emm_bilinear_attn")
     return F1, F2
+
+
+_CORR_GRID = {}
+
+
+def corr_volume_warp(vol0, vol1):
+    """CorrelationVolumeWarping.forward (mapfree_6dreg/lib/models/regression/aggregator.py:42-116; POSITION_ENCODER +
+    MAX_SCORE_CHANNEL).  vol0, vol1 [B,32,H,W] (NCHW or channels_last) -> [B, 67, H, W] = cat[vol0, warped vol1,
+    soft position (2), max score (1)]."""
+    lib = L.load()
+    B, D, H, W = vol0.shape
+    if vol0.shape != vol1.shape:
+        raise AssertionError('Feature volumes shape must match')
+    if vol0.dtype != torch.float32 or vol1.dtype != torch.float32:
+        vol0, vol1 = vol0.float(), vol1.float()
+    if vol0.stride() != vol1.stride() or not (vol0.stride(1) == 1 or vol0.is_contiguous()):
+        vol0, vol1 = vol0.contiguous(), vol1.contiguous()
+    N = H * W
+    if vol0.is_contiguous():
+        sb, sc, sp = D * N, N, 1
+    else:  # channels_last: element (b, c, y, x) at b*sb + (y*W + x)*D + c
+        if vol0.stride() != (N * D, 1, W * D, D):
+            vol0, vol1 = vol0.contiguous(), vol1.contiguous()
+            sb, sc, sp = D * N, N, 1
+        else:
+            sb, sc, sp = N * D, 1, D
+    dev = vol0.device
+    key = (H, W, str(dev))
+    grid = _CORR_GRID.get(key)
+    if grid is None:  # aggregator.py:84-88 (torch.meshgrid default indexing = 'ij')
+        uu, vv = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, W), indexing='ij')
+        grid = torch.stack([uu, vv], dim=0).reshape(2, N).contiguous().to(dev)
+        _CORR_GRID[key] = grid
+    out = torch.empty((B, 2 * D + 3, H, W), dtype=torch.float32, device=dev)
+    ws = _ws(lib.far_corr_volume_warp_workspace_bytes(B, N), dev)
+    with _timed("far_corr_volume_warp"):
+        check(lib.far_corr_volume_warp(ptr(vol0), ptr(vol1), sb, sc, sp, ptr(grid), B, N, D, ptr(out), ptr(ws),
+                                       ws.numel(), stream()), "far_corr_volume_warp")
+    return out
 
 
 def softmax_attention(qkv, num_heads, scale):

@@ -62,6 +62,8 @@ def ransac_round(mkpts0, mkpts1, m_bids, K0, K1, prior_rt=None, batch_size=2048,
     K0, K1 = K0.to(dev).float().contiguous(), K1.to(dev).float().contiguous()
     if offsets is None:
         offsets = ops.segment_offsets(m_bids, N)
+    if mkpts0.shape[0] == 0:   # no match in the whole batch: the kernels still want non-null keypoint pointers
+        mkpts0 = mkpts1 = torch.zeros(1, 2, device=dev)
     prior = prior_rt.to(dev).float().contiguous() if prior_rt is not None else None
     models = ops.ransac_sample_models(mkpts0, mkpts1, offsets, K0, K1, prior if biased else None, bias_sigma_sq,
                                       batch_size, seed)

@@ -63,6 +63,22 @@ def synth_pair_images(n, h=480, w=640, seed=20240000, shift=(8, 16)):
     return torch.from_numpy(img0.astype(np.float32)), torch.from_numpy(img1.astype(np.float32))
 
 
+def synth_mapfree_images(n, seed=20240000):
+    """Map-free inputs: matcher images [n,1,720,544] gray and regression images [n,3,360,270] (bilinear
+    resize of the same texture, per-channel gain, roughly zero-mean like the ImageNet-normalised reference input)."""
+    i0, i1 = synth_pair_images(n, h=720, w=544, seed=seed)
+    gain = torch.tensor([1.0, 0.9, 1.1]).view(1, 3, 1, 1)
+    r0 = torch.nn.functional.interpolate(i0, size=(360, 270), mode="bilinear", align_corners=False).repeat(1, 3, 1, 1)
+    r1 = torch.nn.functional.interpolate(i1, size=(360, 270), mode="bilinear", align_corners=False).repeat(1, 3, 1, 1)
+    return i0, i1, (r0 * gain - 0.45).contiguous(), (r1 * gain - 0.45).contiguous()
+
+
+def mapfree_intrinsics(n=1):
+    """K of the map-free matcher images (f 590, principal point at the image centre of 544 x 720)."""
+    K = torch.tensor([[590.0, 0, 272.0], [0, 590.0, 360.0], [0, 0, 1.0]])
+    return K[None].repeat(n, 1, 1)
+
+
 def mp3d_intrinsics(n=1):
     """K of the Matterport pairs: f 517.97, c (320, 240)  (mp3d_loftr/src/utils/dataset.py:201-211)."""
     K = torch.tensor([[517.97, 0, 320.0], [0, 517.97, 240.0], [0, 0, 1.0]])

@@ -91,6 +91,10 @@ int far_upsample2x_add_nhwc(const float* low, const float* skip, float* out, int
  * (resnet_fpn.py:84-95 layer{1,2}_outconv2).  scale may be NULL (bias only).  x:[pixels, C] NHWC, C % 4 == 0. */
 int far_scale_shift_act_nhwc(float* x, const float* scale, const float* shift, long long pixels, int C,
                              float negative_slope, void* stream);
+/* Out-of-place variant (y != x): the pre-activation `relu(bn(x))` of PreActBlock / PreActBottleneck, where x itself stays
+ * alive as the identity shortcut (mapfree_6dreg/lib/models/regression/encoder/preact.py:35-41, 68-74). */
+int far_scale_shift_act_nhwc_out(const float* x, float* y, const float* scale, const float* shift, long long pixels,
+                                 int C, float negative_slope, void* stream);
 /* Backbone stem: y = relu(conv2d(x, w, stride 2, padding 3) + bias) for a ONE-channel input and a 7x7 kernel,
  * x:[N,1,H,W] fp32, w:[Cout,1,7,7] (eval BatchNorm folded in), y:[N,OH,OW,Cout] NHWC, Cout == 128.
  * Replaces `self.relu(self.bn1(self.conv1(x)))` (mp3d_loftr/src/loftr/backbone/resnet_fpn.py:52-54,80); cuDNN has no
@@ -237,6 +241,18 @@ size_t far_emm_bilinear_attn_workspace_bytes(int B, int Ntok, int h, int d);
 int far_emm_bilinear_attn(const float* qkv1, const float* qkv2, const float* pos, int Bpos, int B, int Ntok,
                           int h, int d, float scale, float* F1, float* F2, int engine, float* workspace,
                           size_t workspace_bytes, void* stream);
+
+/* ---- CorrelationVolumeWarping.forward (mapfree_6dreg/lib/models/regression/aggregator.py:42-116) with the shipped
+ * recipe's flags (POSITION_ENCODER + MAX_SCORE_CHANNEL; config/regression/mapfree/rot6d_trans_with_loftr.yaml:8-11):
+ *   C = softmax_j(vol0^T vol1) [B,N,N];  out = cat[vol0, vol1 C^T, grid C^T, max_j C]  -> [B, 2D+3, N]
+ * vol0, vol1: [B, D, N] given with element strides (sb batch, sc channel, sp pixel): NCHW (sp == 1) or channels_last
+ * (sc == 1); D must be 32 (ENCODER.NUM_OUT_LAYERS of the recipe); grid: [2, N] = the meshgrid(linspace(-1,1,H),
+ * linspace(-1,1,W)) table of :84-88.  Flash-style tcgen05 kernel: the N x N volume (157 MB/pair at N = 6256) is never
+ * written; two sweeps over the key tiles per query tile (exact row maximum, then exponentials + P V'). */
+size_t far_corr_volume_warp_workspace_bytes(int B, int N);
+int far_corr_volume_warp(const float* vol0, const float* vol1, long long sb, long long sc, long long sp,
+                         const float* grid, int B, int N, int D, float* out, float* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* ---- timm-style softmax attention of the 8pt-ViT blocks (vision_transformer.py:236-262):
  * qkv:[B,Ntok,3,h,d] -> out:[B,Ntok,h*d] = softmax(q k^T * scale) v, heads re-interleaved. */

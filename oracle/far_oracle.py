@@ -362,7 +362,8 @@ def compute_normalized_6d(pose_mtx, mean=POSE_MEAN_6D, std=POSE_STD_6D):
     """loftr_loss.py:31-39: [t | R[0,:] | R[1,:]] normalised."""
     r6 = pose_mtx[..., :2, :3].reshape(*pose_mtx.shape[:-2], 6)
     tr = pose_mtx[..., :3, 3]
-    return (torch.cat([tr, r6], dim=-1) - mean) / std
+    v = torch.cat([tr, r6], dim=-1)
+    return (v - mean.to(v.device)) / std.to(v.device)
 
 
 def preprocess_helper(loftr_rt, num_corr, num_before, inl_tight, inl_ultra):
@@ -502,7 +503,7 @@ def far_head_mp3d(p, feat0, feat1, loftr_preds, inv_loftr_preds, cfg):
     pred_reg_6d = _seq(_sub(p, "pose_regressor_simple_moe"), feats, (0, 2), ("relu", None))
     pred_reg_t = pred_reg_6d[..., :3]
     loftr_t_in = loftr_preds[..., :3]
-    mean, std = POSE_MEAN_6D, POSE_STD_6D
+    mean, std = POSE_MEAN_6D.to(loftr_t_in.device), POSE_STD_6D.to(loftr_t_in.device)
     if cfg["regress"]["scale_8pt"]:  # :436-446
         lu = loftr_t_in * std[:3] + mean[:3]
         ru = pred_reg_t * std[:3] + mean[:3]
@@ -522,8 +523,9 @@ def far_head_mp3d(p, feat0, feat1, loftr_preds, inv_loftr_preds, cfg):
 
 def prior_rt_from_regressed(regressed_rt):
     """loftr.py:188-192: de-normalise the head output, Gram-Schmidt, -> priorRT [3,4]."""
-    R = regressed_rt[:, 3:] * POSE_STD_6D[3:] + POSE_MEAN_6D[3:]
-    t = regressed_rt[0, :3] * POSE_STD_6D[:3] + POSE_MEAN_6D[:3]
+    mean, std = POSE_MEAN_6D.to(regressed_rt.device), POSE_STD_6D.to(regressed_rt.device)
+    R = regressed_rt[:, 3:] * std[3:] + mean[3:]
+    t = regressed_rt[0, :3] * std[:3] + mean[:3]
     R = rotation_6d_to_matrix(R)[0]
     return torch.cat([R, t[:, None]], dim=-1)
 

@@ -136,7 +136,8 @@ def install_shims():
              oneway_transfer_error=anyfn, sample_is_valid_for_homography=anyfn)
         _mod("kornia.geometry.solvers", solve_cubic=anyfn)
         _mod("kornia.geometry.linalg", transform_points=anyfn)
-        _mod("kornia.geometry.conversions", convert_points_to_homogeneous=anyfn)
+        _mod("kornia.geometry.conversions", convert_points_to_homogeneous=anyfn, rotation_matrix_to_quaternion=anyfn,
+             quaternion_to_rotation_matrix=anyfn, QuaternionCoeffOrder=types.SimpleNamespace(WXYZ=None))
         _mod("kornia.utils", create_meshgrid=_kornia_create_meshgrid)
         _mod("kornia.utils.grid", create_meshgrid=_kornia_create_meshgrid)
         _mod("kornia.utils.helpers", _torch_svd_cast=anyfn, safe_inverse_with_mask=anyfn,
@@ -261,3 +262,57 @@ def load_vit8pt():
             return ns
         finally:
             pass
+
+
+def _attr_cfg(d):
+    out = _CfgNode()
+    for k, v in d.items():
+        out[k] = _attr_cfg(v) if isinstance(v, dict) else v
+    return out
+
+
+def mapfree_config():
+    """config/regression/mapfree/rot6d_trans_with_loftr.yaml merged over config/default.py (the keys the model reads)."""
+    return _attr_cfg({
+        'MODEL': 'Regression',
+        'ENCODER': {'TYPE': 'ResUNet', 'BLOCK_TYPE': 1, 'NUM_BLOCKS': '3-3-3', 'NOT_CONCAT': False, 'NUM_OUT_LAYERS': 32},
+        'AGGREGATOR': {'TYPE': 'CorrelationVolumeWarping', 'POSITION_ENCODER': True, 'POSITION_ENCODER_IM1': None,
+                       'MAX_SCORE_CHANNEL': True, 'NORMALISE_DOT': False, 'RESIDUAL_ATT': False, 'CV_OUTLAYERS': 0,
+                       'CV_HALF_CHANNELS': False, 'UPSAMPLE_POS_ENC': 0, 'DUSTBIN': False},
+        'HEAD': {'TYPE': 'DirectDeepResBlockMLP', 'ADD_BASIS': True, 'NUM_PTS': 6, 'AVG_POOL': True, 'BATCH_NORM': True,
+                 'SEPARATE_SCALE': True},
+        'TRAINING': {'ROT_LOSS': 'rot_6d_loss', 'TRANS_LOSS': 'trans_unnormalized_loss', 'LAMBDA': 1.},
+        'BACKPROJECT_ANCHORS': False,
+        'DATASET': {'HEIGHT': 360, 'WIDTH': 270},
+        'SOLVER': {'EMAT_RANSAC': {'PIX_THRESHOLD': 2.0, 'SCALE_THRESHOLD': 0.1, 'CONFIDENCE': 0.9999}},
+    })
+
+
+def load_mapfree():
+    """Reference map-free classes: RegressionModel (mapfree_6dreg/lib/models/regression/model.py), the pristine
+    upstream LoFTR it embeds (etc/feature_matching_baselines/LoFTR/src/loftr) and its default_cfg.  torch.load of the
+    (absent) outdoor_ot.ckpt is answered with an empty state dict (strict=False at model.py:105)."""
+    with _subproject("mapfree_6dreg") as root:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("etc",)]:
+            del sys.modules[k]
+        pr = os.path.join(root, "third_party", "prior_ransac")
+        sys.path.insert(0, pr)
+        orig_load = torch.load
+        torch.load = lambda *a, **k: {'state_dict': {}}
+        try:
+            ns = types.SimpleNamespace()
+            mod = importlib.import_module("lib.models.regression.model")
+            ns.model_module = mod
+            ns.RegressionModel = mod.RegressionModel
+            lo = importlib.import_module("etc.feature_matching_baselines.LoFTR.src.loftr")
+            ns.UpstreamLoFTR, ns.upstream_default_cfg = lo.LoFTR, lo.default_cfg
+            ns.build = lambda **kw: _build_mapfree(mod, kw)
+            return ns
+        finally:
+            sys.path.remove(pr)
+            ns.restore = lambda: setattr(torch, "load", orig_load)
+
+
+def _build_mapfree(mod, kw):
+    m = mod.RegressionModel(mapfree_config(), **kw)
+    return m.eval()
