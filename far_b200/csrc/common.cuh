@@ -34,7 +34,7 @@ namespace far {
 enum ProfId {
   PROF_TC_GEMM = 0, PROF_TC_SCORE, PROF_TC_EMM_PV, PROF_LA_REDUCE, PROF_LA_APPLY, PROF_LA_SMALL, PROF_LAYERNORM,
   PROF_LINEAR_SIMT, PROF_FINE_GATHER, PROF_FINE_MATCH, PROF_SPLIT, PROF_EMM_SIMT, PROF_SOLVER, PROF_FPN, PROF_ENC_FUSED,
-  PROF_TC_CORRVOL, PROF_EIGHTPT, PROF_NUM_IDS
+  PROF_TC_CORRVOL, PROF_EIGHTPT, PROF_TC_FLASH_ATTN, PROF_NUM_IDS
 };
 extern bool g_prof_on;
 void prof_begin(int id, double flops, double bytes, cudaStream_t st);
@@ -50,7 +50,31 @@ struct ProfScope {
   }
 };
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+// SM count of the CURRENT device (B200: 148 = 2 dies x 74), queried once per device -- grids of the persistent kernels
+// are sized from it, never from a compile-time constant.
+inline int num_sms() {
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+#define kNumSMs (::far::num_sms())
+// true the first time it is called on the current device with this flag array (cudaFuncSetAttribute is per device)
+inline bool first_use_on_device(bool (&flags)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

@@ -14,6 +14,9 @@
 #include "score.cuh"
 #include "tc_score.cuh"
 #include "tc_emm.cuh"
+#include "tc_flash.cuh"
+#include "tc_gemm.cuh"
+#include <algorithm>
 
 namespace far {
 
@@ -267,13 +270,18 @@ extern "C" int far_emm_bilinear_attn(const float* qkv1, const float* qkv2, const
 
 // timm Attention core (interiornetStreetlearn_8ptVit/src/modules/vision_transformer.py:250-257)
 extern "C" size_t far_softmax_attention_workspace_bytes(int B, int Ntok, int h, int d) {
-  return emm_plan(B, Ntok, h, d).total + 256;
+  size_t n = emm_plan(B, Ntok, h, d).total + 256;
+  if (tc_flash_attention_supported(Ntok, d)) n = std::max(n, tc_flash_attention_bytes(B * h, Ntok, d));
+  return n;
 }
 
 extern "C" int far_softmax_attention(const float* qkv, int B, int Ntok, int h, int d, float scale, float* out,
                                      float* workspace, size_t workspace_bytes, void* stream) {
   if (B <= 0) return FAR_OK;
   FAR_REQUIRE(qkv && out && workspace && Ntok > 0 && h > 0 && d > 0 && d <= 64);
+  // tcgen05 flash kernel (tc_flash.cu) for head dims 32 / 64; FAR_TC=0 or other head dims: CUDA-core two-pass kernels
+  if (tc_engine_default_on() && tc_flash_attention_supported(Ntok, d) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0))
+    return tc_flash_attention(qkv, B, Ntok, h, d, scale, out, workspace, workspace_bytes, (cudaStream_t)stream);
   const EmmPlan pl = emm_plan(B, Ntok, h, d);
   if (workspace_bytes < pl.total) return FAR_ERR_WORKSPACE;
   char* base = reinterpret_cast<char*>(workspace);

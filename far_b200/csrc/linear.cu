@@ -416,7 +416,7 @@ std::vector<ProfRec> g_prof_recs;
 const char* kProfNames[PROF_NUM_IDS] = {
     "tc_gemm_kernel", "tc_score_kernel", "tc_emm_pv_kernel", "la_reduce", "la_apply", "la_small_kernel", "layernorm",
     "linear_simt_kernel", "fine_window_gather_kernel", "fine_match_kernel", "split_kernels", "emm_simt", "solver",
-    "fpn_fuse", "enc_fused_kernel", "tc_corrvol_kernel", "eightpt_kernels"};
+    "fpn_fuse", "enc_fused_kernel", "tc_corrvol_kernel", "eightpt_kernels", "tc_flash_attn_kernel"};
 void prof_clear() {
   for (auto& r : g_prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   g_prof_recs.clear();

@@ -414,11 +414,10 @@ int linear_attention_dispatch(const float* q, int ldq, const float* k, int ldk, 
     const int rec = 32 * 32 + 32;
     float* summed = workspace + (size_t)N * HH * sp2 * rec;
     const size_t sm1 = (size_t)2 * LA2_T * CC * 4, sm2 = ((size_t)LA2_T * CC + HH * (32 * 33) + HH * 32) * 4;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};
+    if (first_use_on_device(attr)) {
       cudaFuncSetAttribute(la_reduce_allheads_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
       cudaFuncSetAttribute(la_apply_allheads_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-      attr = true;
     }
     {
       ProfScope prof(PROF_LA_REDUCE, 2.0 * N * S * CC * 32, 4.0 * 2.0 * N * S * CC, st);
@@ -462,10 +461,9 @@ int la_reduce_summed(const float* k, int ldk, const float* v, int ldv, int N, in
   const int rec = 32 * 32 + 32;
   float* summed = workspace + (size_t)N * HH * sp2 * rec;
   const size_t sm1 = (size_t)2 * LA2_T * CC * 4;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (first_use_on_device(attr)) {
     cudaFuncSetAttribute(la_reduce_allheads_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-    attr = true;
   }
   {
     ProfScope prof(PROF_LA_REDUCE, 2.0 * N * S * CC * 32, 4.0 * 2.0 * N * S * CC, st);

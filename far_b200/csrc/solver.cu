@@ -170,6 +170,70 @@ __global__ void __launch_bounds__(128) eightpt_accumulate_kernel(Pts pts, int P,
   }
 }
 
+// Same record, one CTA (4 warps) per pair: for long correspondence lists (N >= 256) a single warp per pair leaves the
+// kernel latency bound (64 dependent iterations per lane at N = 2048: 8 % of HBM peak); with 128 threads per pair the
+// 2 x 41 KB of a pair are in flight at once and the second pass hits L2.
+template <class Pts>
+__global__ void __launch_bounds__(128) eightpt_accumulate_cta_kernel(Pts pts, int P, double* __restrict__ rec) {
+  __shared__ double sred[4][48];
+  const int pair = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  if (pair >= P) return;
+  const int n = pts.count(pair);
+  double* r = rec + (size_t)pair * kRec;
+  if (n < 8) {
+    if (t == 0) r[51] = (double)n;
+    return;
+  }
+  double sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0;
+  for (int i = t; i < n; i += 128) {
+    float x1, y1, x2, y2, w;
+    pts.load(pair, i, x1, y1, x2, y2, w);
+    sx1 += x1; sy1 += y1; sx2 += x2; sy2 += y2;
+  }
+  sx1 = warp_sum(sx1); sy1 = warp_sum(sy1); sx2 = warp_sum(sx2); sy2 = warp_sum(sy2);
+  if (lane == 0) { sred[wid][0] = sx1; sred[wid][1] = sy1; sred[wid][2] = sx2; sred[wid][3] = sy2; }
+  __syncthreads();
+  // fixed-order merge: every thread computes the same means
+  const double m1x = (sred[0][0] + sred[1][0] + sred[2][0] + sred[3][0]) / n;
+  const double m1y = (sred[0][1] + sred[1][1] + sred[2][1] + sred[3][1]) / n;
+  const double m2x = (sred[0][2] + sred[1][2] + sred[2][2] + sred[3][2]) / n;
+  const double m2y = (sred[0][3] + sred[1][3] + sred[2][3] + sred[3][3]) / n;
+  __syncthreads();
+  double d1 = 0, d2 = 0;
+  double a[45];
+#pragma unroll
+  for (int k = 0; k < 45; ++k) a[k] = 0.0;
+  for (int i = t; i < n; i += 128) {
+    float fx1, fy1, fx2, fy2, fw;
+    pts.load(pair, i, fx1, fy1, fx2, fy2, fw);
+    const double x1 = fx1 - m1x, y1 = fy1 - m1y, x2 = fx2 - m2x, y2 = fy2 - m2y, w = fw;
+    d1 += sqrt(x1 * x1 + y1 * y1);
+    d2 += sqrt(x2 * x2 + y2 * y2);
+    const double X[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1.0};
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < 9; ++p) {
+      const double wp = w * X[p];
+#pragma unroll
+      for (int q = p; q < 9; ++q) { a[k] = fma(wp, X[q], a[k]); ++k; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 45; ++k) {
+    const double v = warp_sum(a[k]);
+    if (lane == 0) sred[wid][k] = v;
+  }
+  d1 = warp_sum(d1); d2 = warp_sum(d2);
+  if (lane == 0) { sred[wid][45] = d1; sred[wid][46] = d2; }
+  __syncthreads();
+  if (t < 47) {
+    const double v = sred[0][t] + sred[1][t] + sred[2][t] + sred[3][t];
+    if (t < 45) r[t] = v;
+    else r[49 + (t - 45)] = sqrt(2.0) / (v / n + 1e-8);   // scale (:739)
+  }
+  if (t == 64) { r[45] = m1x; r[46] = m1y; r[47] = m2x; r[48] = m2y; r[51] = (double)n; }
+}
+
 // ------------------------------------------------------------------------------------------- stage 2
 // F (row-major 3x3, fp32) for one pair from its record.  Returns false when the pair had < 8 points.
 __device__ __forceinline__ bool eightpt_solve(const double* __restrict__ r, float (&F)[9]) {
@@ -736,7 +800,8 @@ extern "C" int far_eight_point(const float* pts1, const float* pts2, const float
   DensePts pts{pts1, pts2, weights, counts, N};
   // algorithmic bytes: 20 N in (two point sets + weight) + 36 out per pair; ~120 N FLOP
   ProfScope prof(PROF_EIGHTPT, 120.0 * N * (double)P, ((weights ? 20.0 : 16.0) * N + 36.0) * (double)P, st);
-  eightpt_accumulate_kernel<DensePts><<<ceil_div(P, 4), 128, 0, st>>>(pts, P, rec);
+  if (N >= 256) eightpt_accumulate_cta_kernel<DensePts><<<P, 128, 0, st>>>(pts, P, rec);
+  else eightpt_accumulate_kernel<DensePts><<<ceil_div(P, 4), 128, 0, st>>>(pts, P, rec);
   FAR_CHECK_LAUNCH();
   eightpt_solve_kernel<<<ceil_div(P, 64), 64, 0, st>>>(rec, P, F);
   FAR_CHECK_LAUNCH();

@@ -442,10 +442,9 @@ int tc_emm_pv(const float* qhi, const float* qlo, const float* khi, const float*
       !make_map4(&mKhi, khi, d, N, d, H, gs, nbat, bs, EBJ) || !make_map4(&mKlo, klo, d, N, d, H, gs, nbat, bs, EBJ) ||
       !make_map_vt(&mVhi, vthi, Npad, G) || !make_map_vt(&mVlo, vtlo, Npad, G))
     return FAR_ERR_CUDA;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (first_use_on_device(attr)) {
     cudaFuncSetAttribute(tc_emm_pv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMM_SMEM);
-    attr = true;
   }
   EmmTcArgs p{G, H, N, d, scale, rowlse, collse, v, sb, sh, ldv, pos, Bpos, Fpart};
   ProfScope prof(PROF_TC_EMM_PV, (double)G * (2.0 * N * N * d + 2.0 * N * N * (d + 6) + 2.0 * N * (d + 6) * (d + 6)),

@@ -1,3 +1,8 @@
+// Flash-style softmax(Q K^T) V on tcgen05 for the two places the path has a plain (single-direction) softmax attention:
+//   * timm Attention of the 8pt-ViT blocks (interiornetStreetlearn_8ptVit/src/modules/vision_transformer.py:250-257,
+//     N = 576, 3 heads x 64) and nn.MultiheadAttention of the map-free TransformerEncoder (model.py:57-61, 108 tokens,
+//     8 heads x 32): far_softmax_attention  -> tc_flash_kernel<KB, DV, MODE_ATTN>
+//   * the map-free correlation-volume aggregator, below                       -> tc_flash_kernel<1, 48, MODE_CORR>
 // Map-free correlation-volume aggregator on tcgen05, flash style (never materialises the [HW, HW] volume):
 //   mapfree_6dreg/lib/models/regression/aggregator.py:42-116  `CorrelationVolumeWarping.forward` with the shipped
 //   recipe's flags (config/regression/mapfree/rot6d_trans_with_loftr.yaml:8-11: POSITION_ENCODER, MAX_SCORE_CHANNEL;
@@ -20,21 +25,26 @@
 namespace far {
 namespace tc {
 
-constexpr int CD = 32;                      // feature channels (ENCODER.NUM_OUT_LAYERS of the recipe)
+constexpr int CD = 32;                      // correlation volume: feature channels (ENCODER.NUM_OUT_LAYERS of the recipe)
 constexpr int CBJ = 64;                     // keys per j-tile
-constexpr int CDV = 48;                     // value channels padded to the MMA N granularity (32 + 2 grid + 14 zero)
-constexpr int C_Q_BYTES = 2 * TILE_BYTES;   // Q hi, lo: [128 x 32 floats] each
+constexpr int CDV = 48;                     // correlation volume: value channels padded to the MMA N granularity (32 + 2 grid + 14 zero)
 constexpr int C_KT = CBJ * BK * 4;          // 8 KiB: one K box [64 keys x 32 floats]
-constexpr int C_VT = CDV * BK * 4;          // 6 KiB: one V'^T box [48 channels x 32 keys]
-constexpr int C_K_STAGE = 2 * C_KT;         // hi, lo
-constexpr int C_V_STAGE = 4 * C_VT;         // 2 key blocks x (hi, lo)
-constexpr int C_NST = 4;                    // ring depth (K and V' rings are independent)
 constexpr int C_BAR_BYTES = 1024;
+constexpr int MODE_CORR = 0, MODE_ATTN = 1;
+// per-instantiation geometry: KB = 32-float k-blocks of the head dimension (1: d = 32, 2: d = 64), DV = value channels
+template <int KB, int DV>
+struct FlashCfg {
+  static constexpr int Q_BYTES = KB * 2 * TILE_BYTES;    // per k-block: Q hi, lo [128 x 32 floats]
+  static constexpr int VT = DV * BK * 4;                 // one V^T box [DV channels x 32 keys]
+  static constexpr int K_STAGE = KB * 2 * C_KT;          // per k-block: hi, lo (adjacent: one N = 128 instruction)
+  static constexpr int V_STAGE = 4 * VT;                 // 2 key blocks x (hi, lo)
+  static constexpr int NST = (KB == 1) ? 4 : 2;          // ring depth (K and V rings are independent)
+  static constexpr size_t SMEM = 1024 + Q_BYTES + NST * (K_STAGE + V_STAGE) + C_BAR_BYTES + 4 * BM * 4;
+};
 constexpr int C_SM_WARPS = 16;              // softmax warps: 4 per TMEM lane quarter, 16 keys each
 constexpr int C_SM_THREADS = 32 * C_SM_WARPS;
 constexpr int C_CW = CBJ / (C_SM_WARPS / 4);  // 16 key columns per softmax thread
 constexpr int C_THREADS = 64 + C_SM_THREADS;
-constexpr size_t CORR_SMEM = 1024 + C_Q_BYTES + C_NST * (C_K_STAGE + C_V_STAGE) + C_BAR_BYTES + 4 * BM * 4;
 
 __host__ __device__ constexpr uint32_t c_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -78,19 +88,24 @@ __device__ __forceinline__ float c_ex2(float x) {
 }
 
 struct CorrArgs {
-  int B, N, Cout;   // batch, tokens, output channels (2*CD + 3)
-  float* out;       // [B, Cout, N]
+  int B, N, Cout;   // groups (batch, or batch * heads), tokens; MODE_CORR: output channels (2*CD + 3)
+  float* out;       // MODE_CORR: [B, Cout, N];  MODE_ATTN: [B / H, N, H * DV]
+  int H;            // MODE_ATTN: heads per batch element
+  float scale;      // MODE_ATTN: softmax(scale * q k^T)
 };
 
+template <int KB, int DV, int MODE>
 __global__ void __launch_bounds__(C_THREADS, 1)
-tc_corrvol_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant__ CUtensorMap mapQlo,
+tc_flash_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant__ CUtensorMap mapQlo,
                   const __grid_constant__ CUtensorMap mapKhi, const __grid_constant__ CUtensorMap mapKlo,
                   const __grid_constant__ CUtensorMap mapVhi, const __grid_constant__ CUtensorMap mapVlo, CorrArgs p) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
+  using Cfg = FlashCfg<KB, DV>;
+  constexpr int C_NST = Cfg::NST, C_K_STAGE = Cfg::K_STAGE, C_V_STAGE = Cfg::V_STAGE, C_VT = Cfg::VT;
   const uint32_t q_base = base;
-  const uint32_t k_base = base + C_Q_BYTES;
+  const uint32_t k_base = base + Cfg::Q_BYTES;
   const uint32_t v_base = k_base + C_NST * C_K_STAGE;
   const uint32_t bar_base = v_base + C_NST * C_V_STAGE;
   const uint32_t q_full = bar_base + 0, t_full = bar_base + 8;
@@ -128,22 +143,28 @@ tc_corrvol_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   auto tSP = [&](int s) { return tmem_base + (uint32_t)(s * 128); };
-  const uint32_t tT_main = tmem_base + 256, tT_cross = tmem_base + 320;
+  const uint32_t tT_main = tmem_base + 256, tT_cross = tmem_base + 256 + 64;   // DV <= 64
 
   if (warp == 0) {
     // ===================== TMA producer: lane 0 streams K tiles (both sweeps), lane 1 the V'^T tiles (sweep 2) =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, C_Q_BYTES);
-      tma_load_4d(q_base, &mapQhi, q_full, 0, i0, 0, b);
-      tma_load_4d(q_base + TILE_BYTES, &mapQlo, q_full, 0, i0, 0, b);
+      mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        tma_load_4d(q_base + (kb * 2 + 0) * TILE_BYTES, &mapQhi, q_full, kb * BK, i0, 0, b);
+        tma_load_4d(q_base + (kb * 2 + 1) * TILE_BYTES, &mapQlo, q_full, kb * BK, i0, 0, b);
+      }
       for (int t = 0; t < NT; ++t) {
         const int jt = t < JT ? t : t - JT;
         const int st = t % C_NST;
         mbar_wait(k_empty(st), (uint32_t)(((t / C_NST) & 1) ^ 1));
         const uint32_t kb = k_base + st * C_K_STAGE;
         mbar_arrive_expect_tx(k_full(st), C_K_STAGE);
-        tma_load_4d(kb, &mapKhi, k_full(st), 0, jt * CBJ, 0, b);
-        tma_load_4d(kb + C_KT, &mapKlo, k_full(st), 0, jt * CBJ, 0, b);
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+          tma_load_4d(kb + (q * 2 + 0) * C_KT, &mapKhi, k_full(st), q * BK, jt * CBJ, 0, b);
+          tma_load_4d(kb + (q * 2 + 1) * C_KT, &mapKlo, k_full(st), q * BK, jt * CBJ, 0, b);
+        }
       }
     } else if (lane == 1) {
       for (int jt = 0; jt < JT; ++jt) {
@@ -159,10 +180,9 @@ tc_corrvol_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp in the loop, one elected lane issues) =====================
-    constexpr uint32_t idS = c_idesc(BM, CBJ), idS2 = c_idesc(BM, 2 * CBJ), idT = c_idesc(BM, CDV);
+    constexpr uint32_t idS = c_idesc(BM, CBJ), idS2 = c_idesc(BM, 2 * CBJ), idT = c_idesc(BM, DV);
     mbar_wait(q_full, 0);
     tc_fence_after();
-    const uint64_t dQhi = make_kmajor_sw128_desc(q_base), dQlo = make_kmajor_sw128_desc(q_base + TILE_BYTES);
     auto issue_S = [&](int t) {   // S(t) = Q K(t)^T into S/P buffer t & 1
       const int st = t % C_NST;
       mbar_wait(k_full(st), (uint32_t)((t / C_NST) & 1));
@@ -170,13 +190,18 @@ tc_corrvol_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_const
       if (elect_one()) {
         const uint32_t kb = k_base + st * C_K_STAGE;
         const uint32_t tS_main = tSP(t & 1), tS_cross = tSP(t & 1) + 64;
-        const uint64_t dKhi = make_kmajor_sw128_desc(kb);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-          // [S_main | S_cross] += Qhi x [Khi ; Klo] as one N = 128 instruction (K hi/lo boxes adjacent in shared memory)
-          umma_tf32(tS_main, dQhi + koff, dKhi + koff, idS2, k ? 1u : 0u);
-          umma_tf32(tS_cross, dQlo + koff, dKhi + koff, idS, 1u);
+        for (int q = 0; q < KB; ++q) {
+          const uint64_t dQhi = make_kmajor_sw128_desc(q_base + (q * 2 + 0) * TILE_BYTES);
+          const uint64_t dQlo = make_kmajor_sw128_desc(q_base + (q * 2 + 1) * TILE_BYTES);
+          const uint64_t dKhi = make_kmajor_sw128_desc(kb + (q * 2) * C_KT);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+            // [S_main | S_cross] += Qhi x [Khi ; Klo] as one N = 128 instruction (K hi/lo boxes adjacent in shared memory)
+            umma_tf32(tS_main, dQhi + koff, dKhi + koff, idS2, (q | k) ? 1u : 0u);
+            umma_tf32(tS_cross, dQlo + koff, dKhi + koff, idS, 1u);
+          }
         }
         umma_commit(s_full(t & 1));
         umma_commit(k_empty(st));
@@ -226,7 +251,7 @@ tc_corrvol_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_const
     const int row = quarter * 32 + lane;
     const int grow = i0 + row;
     const bool rvalid = grow < p.N;
-    constexpr float kL2e = 1.4426950408889634f;
+    const float kL2e = 1.4426950408889634f * (MODE == MODE_ATTN ? p.scale : 1.f);   // scale > 0: same arg max
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     // ---- sweep 1: exact row maximum
     float m = -INFINITY;
@@ -287,24 +312,47 @@ tc_corrvol_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_const
     red[cgp][row] = l;
     c_bar2();
     const float inv = 1.f / (red[0][row] + red[1][row] + red[2][row] + red[3][row]);
-    // ---- epilogue: out[b, CD + c, i] = T[i, c] / l  (c < CD + 2);  out[b, 2CD+2, i] = 1 / l
     mbar_wait(t_full, 0);
     tc_fence_after();
-    float* ob = p.out + (size_t)b * p.Cout * p.N;
-    if (cgp < 3) {
-      uint32_t a[16], c[16];
-      c_ld16(tT_main + lane_off + (uint32_t)(cgp * 16), a);
-      c_ld16(tT_cross + lane_off + (uint32_t)(cgp * 16), c);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (rvalid) {
+    if (MODE == MODE_CORR) {
+      // ---- out[b, CD + c, i] = T[i, c] / l  (c < CD + 2);  out[b, 2CD+2, i] = 1 / l   (channel-major: lanes = tokens)
+      float* ob = p.out + (size_t)b * p.Cout * p.N;
+      if (cgp < 3) {
+        uint32_t a[16], c[16];
+        c_ld16(tT_main + lane_off + (uint32_t)(cgp * 16), a);
+        c_ld16(tT_cross + lane_off + (uint32_t)(cgp * 16), c);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (rvalid) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int ch = cgp * 16 + e;
-          if (ch < CD + 2) ob[(size_t)(CD + ch) * p.N + grow] = (__uint_as_float(a[e]) + __uint_as_float(c[e])) * inv;
+          for (int e = 0; e < 16; ++e) {
+            const int ch = cgp * 16 + e;
+            if (ch < CD + 2) ob[(size_t)(CD + ch) * p.N + grow] = (__uint_as_float(a[e]) + __uint_as_float(c[e])) * inv;
+          }
+        }
+      } else if (rvalid) {
+        ob[(size_t)(2 * CD + 2) * p.N + grow] = inv;
+      }
+    } else {
+      // ---- out[bb, i, h * DV + c] = T[i, c] / l   (token-major, heads re-interleaved: each thread owns 16-float runs)
+      const int bb = b / p.H, hh = b % p.H;
+      float* orow = p.out + ((size_t)bb * p.N + grow) * ((size_t)p.H * DV) + (size_t)hh * DV;
+      for (int cc = cgp; cc < DV / 16; cc += 4) {
+        uint32_t a[16], c[16];
+        c_ld16(tT_main + lane_off + (uint32_t)(cc * 16), a);
+        c_ld16(tT_cross + lane_off + (uint32_t)(cc * 16), c);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (rvalid) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            float4 v;
+            v.x = (__uint_as_float(a[e]) + __uint_as_float(c[e])) * inv;
+            v.y = (__uint_as_float(a[e + 1]) + __uint_as_float(c[e + 1])) * inv;
+            v.z = (__uint_as_float(a[e + 2]) + __uint_as_float(c[e + 2])) * inv;
+            v.w = (__uint_as_float(a[e + 3]) + __uint_as_float(c[e + 3])) * inv;
+            *reinterpret_cast<float4*>(orow + cc * 16 + e) = v;
+          }
         }
       }
-    } else if (rvalid) {
-      ob[(size_t)(2 * CD + 2) * p.N + grow] = inv;
     }
   }
 
@@ -380,19 +428,107 @@ __global__ void corrvol_prep_kernel(const float* __restrict__ vol0, const float*
   }
 }
 
-static bool make_map_vt48(CUtensorMap* map, const float* ptr, int Npad, int B) {
+static bool make_map_vt(CUtensorMap* map, const float* ptr, int Npad, int DV, int B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
-  cuuint64_t gdim[3] = {(cuuint64_t)Npad, (cuuint64_t)CDV, (cuuint64_t)B};
-  cuuint64_t gstr[2] = {(cuuint64_t)Npad * 4, (cuuint64_t)Npad * CDV * 4};
-  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)CDV, 1};
+  cuuint64_t gdim[3] = {(cuuint64_t)Npad, (cuuint64_t)DV, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)Npad * 4, (cuuint64_t)Npad * DV * 4};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)DV, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Attention operand preparation: qkv [B, N, 3, H, d] (the fused qkv Linear's output) -> token-major hi/lo of q and k
+// [G = B*H, N, d] and channel-major hi/lo of v^T [G, d, Npad].  grid (ceil(Npad/32), d/32, G), block (32, 8).
+__global__ void attn_prep_kernel(const float* __restrict__ qkv, int N, int Npad, int H, int d, float* __restrict__ qhi,
+                                 float* __restrict__ qlo, float* __restrict__ khi, float* __restrict__ klo,
+                                 float* __restrict__ vthi, float* __restrict__ vtlo) {
+  __shared__ float tv[32][33];   // [token][channel]
+  const int g = blockIdx.z, bb = g / H, hh = g % H, c0 = blockIdx.y * 32, tok0 = blockIdx.x * 32;
+  const int C = H * d, tx = threadIdx.x;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int tok = tok0 + r;
+    float q = 0.f, k = 0.f, v = 0.f;
+    if (tok < N) {
+      const float* row = qkv + ((size_t)bb * N + tok) * 3 * C + (size_t)hh * d + c0 + tx;
+      q = row[0]; k = row[C]; v = row[2 * C];
+      const size_t o = ((size_t)g * N + tok) * d + c0 + tx;
+      const float qh = __uint_as_float(__float_as_uint(q) & 0xFFFFE000u);
+      const float kh = __uint_as_float(__float_as_uint(k) & 0xFFFFE000u);
+      qhi[o] = qh; qlo[o] = q - qh;
+      khi[o] = kh; klo[o] = k - kh;
+    }
+    tv[r][tx] = v;
+  }
+  __syncthreads();
+  for (int c = threadIdx.y; c < 32; c += 8) {   // threadIdx.x = token: contiguous in v^T
+    const int tok = tok0 + tx;
+    if (tok < Npad) {
+      const float v = tv[tx][c];
+      const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      const size_t o = ((size_t)g * d + c0 + c) * Npad + tok;
+      vthi[o] = h;
+      vtlo[o] = v - h;
+    }
+  }
+}
+
+template <int KB, int DV, int MODE>
+static int launch_flash(const float* qhi, const float* qlo, const float* khi, const float* klo, const float* vthi,
+                        const float* vtlo, int G, int N, int Npad, const CorrArgs& p, cudaStream_t st) {
+  constexpr int d = KB * BK;
+  CUtensorMap mQhi, mQlo, mKhi, mKlo, mVhi, mVlo;
+  const long long bs = (long long)N * d;
+  if (!make_map4(&mQhi, qhi, d, N, d, 1, bs, G, bs, BM) || !make_map4(&mQlo, qlo, d, N, d, 1, bs, G, bs, BM) ||
+      !make_map4(&mKhi, khi, d, N, d, 1, bs, G, bs, CBJ) || !make_map4(&mKlo, klo, d, N, d, 1, bs, G, bs, CBJ) ||
+      !make_map_vt(&mVhi, vthi, Npad, DV, G) || !make_map_vt(&mVlo, vtlo, Npad, DV, G))
+    return FAR_ERR_CUDA;
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set))
+    cudaFuncSetAttribute(tc_flash_kernel<KB, DV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)FlashCfg<KB, DV>::SMEM);
+  tc_flash_kernel<KB, DV, MODE><<<dim3(ceil_div(N, BM), G), C_THREADS, FlashCfg<KB, DV>::SMEM, st>>>(mQhi, mQlo, mKhi, mKlo,
+                                                                                                   mVhi, mVlo, p);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
 }  // namespace tc
+
+// ---- softmax attention (far_softmax_attention, emm.cu) on the flash kernel: d = 32 or 64 -----------------------------
+bool tc_flash_attention_supported(int N, int d) { return (d == 32 || d == 64) && N >= 1 && tc::get_encode() != nullptr; }
+
+size_t tc_flash_attention_bytes(int G, int N, int d) {
+  const int Npad = (N + 3) & ~3;
+  return 4 * tc::al((size_t)G * N * d * 4) + 2 * tc::al((size_t)G * d * Npad * 4) + 2048;
+}
+
+int tc_flash_attention(const float* qkv, int B, int N, int H, int d, float scale, float* out, float* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
+  using namespace tc;
+  const int G = B * H, Npad = (N + 3) & ~3;
+  if (workspace_bytes < tc_flash_attention_bytes(G, N, d)) return FAR_ERR_WORKSPACE;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  const size_t qb = al((size_t)G * N * d * 4), vb = al((size_t)G * d * Npad * 4);
+  float* qhi = reinterpret_cast<float*>(base);
+  float* qlo = reinterpret_cast<float*>(base + qb);
+  float* khi = reinterpret_cast<float*>(base + 2 * qb);
+  float* klo = reinterpret_cast<float*>(base + 3 * qb);
+  float* vthi = reinterpret_cast<float*>(base + 4 * qb);
+  float* vtlo = reinterpret_cast<float*>(base + 4 * qb + vb);
+  attn_prep_kernel<<<dim3(ceil_div(Npad, 32), d / 32, G), dim3(32, 8), 0, st>>>(qkv, N, Npad, H, d, qhi, qlo, khi, klo,
+                                                                                vthi, vtlo);
+  FAR_CHECK_LAUNCH();
+  CorrArgs p{G, N, 0, out, H, scale};
+  // algorithmic work: S = q k^T twice (row-maximum sweep + recompute) + P V; bytes: qkv in, out
+  ProfScope prof(PROF_TC_FLASH_ATTN, (double)G * (2.0 * 2.0 * N * (double)N * d + 2.0 * N * (double)N * d),
+                 4.0 * G * 4.0 * (double)N * d, st);
+  if (d == 64) return launch_flash<2, 64, MODE_ATTN>(qhi, qlo, khi, klo, vthi, vtlo, G, N, Npad, p, st);
+  return launch_flash<1, 32, MODE_ATTN>(qhi, qlo, khi, klo, vthi, vtlo, G, N, Npad, p, st);
+}
+
 }  // namespace far
 
 using namespace far;
@@ -426,24 +562,9 @@ extern "C" int far_corr_volume_warp(const float* vol0, const float* vol1, long l
   corrvol_prep_kernel<<<dim3(ceil_div(Npad, 32), B), dim3(32, 8), 0, st>>>(vol0, vol1, sb, sc, sp, grid, N, Npad, qhi, qlo,
                                                                            khi, klo, vthi, vtlo, out, Cout);
   FAR_CHECK_LAUNCH();
-  CUtensorMap mQhi, mQlo, mKhi, mKlo, mVhi, mVlo;
-  const long long bs = (long long)N * CD;
-  if (!make_map4(&mQhi, qhi, CD, N, CD, 1, bs, B, bs, BM) || !make_map4(&mQlo, qlo, CD, N, CD, 1, bs, B, bs, BM) ||
-      !make_map4(&mKhi, khi, CD, N, CD, 1, bs, B, bs, CBJ) || !make_map4(&mKlo, klo, CD, N, CD, 1, bs, B, bs, CBJ) ||
-      !make_map_vt48(&mVhi, vthi, Npad, B) || !make_map_vt48(&mVlo, vtlo, Npad, B))
-    return FAR_ERR_CUDA;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  static bool attr_set[64] = {};
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaFuncSetAttribute(tc_corrvol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CORR_SMEM);
-    attr_set[dev] = true;
-  }
-  CorrArgs p{B, N, Cout, out};
+  CorrArgs p{B, N, Cout, out, 1, 1.f};
   // algorithmic work: S twice (row-max sweep + recompute) + P V';  bytes: vol0, vol1 in, 2D+3 channels out
   ProfScope prof(PROF_TC_CORRVOL, (double)B * (2.0 * 2.0 * N * (double)N * CD + 2.0 * N * (double)N * (CD + 2)),
                  4.0 * B * ((double)N * 2 * CD + (double)N * Cout), st);
-  tc_corrvol_kernel<<<dim3(ceil_div(N, BM), B), C_THREADS, CORR_SMEM, st>>>(mQhi, mQlo, mKhi, mKlo, mVhi, mVlo, p);
-  FAR_CHECK_LAUNCH();
-  return FAR_OK;
+  return launch_flash<1, CDV, MODE_CORR>(qhi, qlo, khi, klo, vthi, vtlo, B, N, Npad, p, st);
 }

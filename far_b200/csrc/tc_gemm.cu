@@ -400,9 +400,8 @@ __global__ void split_tf32_kernel(const float* __restrict__ x1, int ld1, int K1,
 
 EncodeTiledFn get_encode() {
   static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static bool tried[64] = {};
+  if (first_use_on_device(tried)) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
@@ -531,11 +530,10 @@ int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
   // output: dims (N, L, G, 1), 32 x 32 boxes, SWIZZLE_128B staging
   ok = ok && make_map4(&mC, a.y, N, L, a.ldy, G, (long long)L * a.ldy, 1, (long long)M * a.ldy, 32);
   if (!ok) return FAR_ERR_CUDA;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-    attr_set = true;
   }
   static const int dbg = getenv("FAR_TC_DBG") ? atoi(getenv("FAR_TC_DBG")) : 0;
   GemmArgs p{};

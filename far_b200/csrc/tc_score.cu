@@ -546,11 +546,10 @@ static int prepare_operands(const ScoreArgs& a, float* ws, size_t ws_bytes, Spli
 }
 
 static void set_attr_once() {
-  static bool done = false;
-  if (!done) {
+  static bool done[64] = {};
+  if (first_use_on_device(done)) {
     cudaFuncSetAttribute(tc_score_kernel<MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM);
     cudaFuncSetAttribute(tc_score_kernel<MODE_CONF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM);
-    done = true;
   }
 }
 
@@ -602,10 +601,9 @@ int tc_lse64_partials(const ScoreArgs& a, float2* rowpart, float2* colpart, floa
   CUtensorMap maps[4];
   int rc = prepare_operands(a, ws, ws_bytes, &o, maps, split_done, st);
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (first_use_on_device(attr)) {
     cudaFuncSetAttribute(tc_lse64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LSE64_SMEM);
-    attr = true;
   }
   Lse64Args p{a.G, a.H, a.L, a.S, a.scale * kLog2e, rowpart, colpart};
   ProfScope prof(PROF_TC_SCORE, 2.0 * a.G * a.L * a.S * a.K, 4.0 * a.G * ((double)a.L + a.S) * a.K, st);

@@ -26,7 +26,9 @@ class CoarseMatching(nn.Module):
         self.materialize_conf_matrix = bool(config.get('materialize_conf_matrix', False))
         self.engine = ENGINE_AUTO
 
-    def forward(self, feat_c0, feat_c1, data, mask_c0=None, mask_c1=None):
+    def forward_begin(self, feat_c0, feat_c1, data, mask_c0=None, mask_c1=None):
+        """Launch the score / decision kernels and the asynchronous read-back of the match count; returns a handle for
+        forward_end().  GPU work queued in between overlaps the host's wait for M (ops.dual_softmax_match_begin)."""
         if mask_c0 is not None or 'mask0' in data:
             raise NotImplementedError("padding masks (MegaDepth) are outside the FAR eval path")
         if self.training:
@@ -34,11 +36,17 @@ class CoarseMatching(nn.Module):
         scale = data['hw0_i'][0] / data['hw0_c'][0]
         if 'scale0' in data:
             raise NotImplementedError("per-image scale0/scale1 (MegaDepth resize) is outside the FAR eval path")
-        m = ops.dual_softmax_match(feat_c0, feat_c1, tuple(data['hw0_c']), tuple(data['hw1_c']), self.thr,
-                                   self.border_rm, self.temperature, scale, scale,
-                                   return_conf_matrix=self.materialize_conf_matrix, engine=self.engine)
+        return ops.dual_softmax_match_begin(feat_c0, feat_c1, tuple(data['hw0_c']), tuple(data['hw1_c']), self.thr,
+                                            self.border_rm, self.temperature, scale, scale,
+                                            return_conf_matrix=self.materialize_conf_matrix, engine=self.engine)
+
+    def forward_end(self, handle, data):
+        m = ops.dual_softmax_match_end(handle)
         data.update({'conf_matrix': m.get('conf_matrix'),
                      'b_ids': m['b_ids'], 'i_ids': m['i_ids'], 'j_ids': m['j_ids'],
                      'gt_mask': torch.zeros_like(m['mconf'], dtype=torch.bool),   # mconf == 0 never survives (:258)
                      'm_bids': m['b_ids'], 'mkpts0_c': m['mkpts0_c'], 'mkpts1_c': m['mkpts1_c'],
                      'mconf': m['mconf']})
+
+    def forward(self, feat_c0, feat_c1, data, mask_c0=None, mask_c1=None):
+        self.forward_end(self.forward_begin(feat_c0, feat_c1, data, mask_c0, mask_c1), data)

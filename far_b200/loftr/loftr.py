@@ -54,19 +54,30 @@ class LoFTR(nn.Module):
                      'feats_c': feats_c})
 
     # ------------------------------------------------------------------ 2-5. transformer + matching (CUDA kernels)
-    def forward_correspondence_prediction(self, data, train=False):
+    def forward_coarse(self, data):
+        """Positional encoding -> coarse LoFTR -> score / decision kernels of the coarse matcher.  Stops before the
+        reference's host sync on the match count (coarse_matching.py:193): returns the handle forward_fine() completes,
+        so a caller can queue work that only needs the coarse features (the FAR head trunk) in between."""
         if 'mask0' in data:
             raise NotImplementedError("padding masks (MegaDepth) are outside the FAR eval path")
         feat_c0 = self.pos_encoding.forward_flatten(data['featmap0'])   # [N, HW, C]
         feat_c1 = self.pos_encoding.forward_flatten(data['featmap1'])
         feat_c0, feat_c1 = self.loftr_coarse(feat_c0, feat_c1)
-        self.coarse_matching(feat_c0, feat_c1, data)
+        handle = self.coarse_matching.forward_begin(feat_c0, feat_c1, data)
+        data.update({'featmap0': feat_c0, 'featmap1': feat_c1, 'mask_c0': None, 'mask_c1': None,
+                     'translation_scale': None})
+        return handle
+
+    def forward_fine(self, data, handle, train=False):
+        feat_c0, feat_c1 = data['featmap0'], data['featmap1']
+        self.coarse_matching.forward_end(handle, data)
         ff0, ff1 = self.fine_preprocess(data['featmap_f0'], data['featmap_f1'], feat_c0, feat_c1, data)
         if ff0.size(0) != 0:
             ff0, ff1 = self.loftr_fine(ff0, ff1)
         self.fine_matching(ff0, ff1, data, train=train)
-        data.update({'featmap0': feat_c0, 'featmap1': feat_c1, 'mask_c0': None, 'mask_c1': None,
-                     'translation_scale': None})
+
+    def forward_correspondence_prediction(self, data, train=False):
+        self.forward_fine(data, self.forward_coarse(data), train=train)
 
     # ------------------------------------------------------------------ 6. FAR head
     def preprocess_helper(self, data):
@@ -100,6 +111,22 @@ class LoFTR(nn.Module):
                 inv_loftr_preds_6d = torch.cat([inv_loftr_preds_6d, e], dim=-1)
         return feat_c0, feat_c1, None, None, loftr_preds_6d, inv_loftr_preds_6d
 
+    def head_trunk(self, data, feat_c0=None, feat_c1=None):
+        """The solver-independent part of the FAR head on data['featmap0/1'] (post coarse transformer), cached in `data`
+        for the current forward when config['regress']['reuse_trunk'] (default).  May be called right after
+        forward_coarse(): it does not need the matches."""
+        feat_c0 = data['featmap0'] if feat_c0 is None else feat_c0
+        feat_c1 = data['featmap1'] if feat_c1 is None else feat_c1
+        reuse = self.config['regress'].get('reuse_trunk', True)
+        key = (feat_c0.data_ptr(), feat_c1.data_ptr(), feat_c0._version, feat_c1._version, tuple(feat_c0.shape))
+        cached = data.get('_far_head_trunk') if reuse else None
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        trunk = self.loftr_regress.forward_trunk(feat_c0, feat_c1)
+        if reuse:
+            data['_far_head_trunk'] = (key, trunk, feat_c0, feat_c1)  # holds the maps: storage cannot be recycled
+        return trunk
+
     def forward_rt_prediction(self, data):
         if not self.config['regress_rt']:
             return
@@ -109,15 +136,7 @@ class LoFTR(nn.Module):
         # prediction (lightning_loftr.py:338-346).  Within one forward (one `data` dict) the trunk is evaluated once and
         # reused; outputs are identical to re-evaluating it (tests/test_gpu_parity.py::test_head_trunk_reuse).
         # config['regress']['reuse_trunk'] = False restores the literal re-evaluation.
-        reuse = self.config['regress'].get('reuse_trunk', True)
-        key = (feat_c0.data_ptr(), feat_c1.data_ptr(), feat_c0._version, feat_c1._version, tuple(feat_c0.shape))
-        cached = data.get('_far_head_trunk') if reuse else None
-        if cached is not None and cached[0] == key:
-            trunk = cached[1]
-        else:
-            trunk = self.loftr_regress.forward_trunk(feat_c0, feat_c1)
-            if reuse:
-                data['_far_head_trunk'] = (key, trunk, feat_c0, feat_c1)  # holds the maps: storage cannot be recycled
+        trunk = self.head_trunk(data, feat_c0, feat_c1)
         pred_RT, mlp_features, pred_RT_wt = self.loftr_regress.forward_gate(trunk, loftr_preds=lp, inv_loftr_preds=ilp)
         data.update({'regressed_rt': pred_RT, 'expec_rt': pred_RT[0]})
         if self.config['regress']['save_mlp_feats']:

@@ -224,38 +224,86 @@ def loftr_encoder_layer(x, source, weights, nhead, engine=L.ENGINE_AUTO):
     return out
 
 
-def dual_softmax_match(feat_c0, feat_c1, hw0_c, hw1_c, thr, border_rm, temperature, scale0, scale1,
-                       return_conf_matrix=False, engine=L.ENGINE_AUTO):
-    """CoarseMatching.forward + get_coarse_match (coarse_matching.py:86-265), dual-softmax, eval.
-    Returns dict(b_ids,i_ids,j_ids,mconf,mkpts0_c,mkpts1_c[,conf_matrix]).  One device->host sync for M, as in the
-    reference's torch.where (:193)."""
+class _MatchHandle:
+    """State between far_dual_softmax_match_select and _gather (the match count M is data dependent)."""
+    __slots__ = ("ws", "nws", "cnt", "cnt_host", "event", "conf", "shape", "hw", "scales", "dev")
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
+def dual_softmax_match_begin(feat_c0, feat_c1, hw0_c, hw1_c, thr, border_rm, temperature, scale0, scale1,
+                             return_conf_matrix=False, engine=L.ENGINE_AUTO):
+    """First half of CoarseMatching (coarse_matching.py:86-193): launches the score / decision kernels and starts an
+    asynchronous read-back of the match count on a side stream.  The caller may queue more GPU work (e.g. the FAR head
+    trunk, which only needs the coarse features) before calling dual_softmax_match_end(): the host then learns M while
+    the GPU is still busy, instead of draining the stream at the reference's torch.where sync point (:193)."""
     lib = L.load()
     N, Lq, C = feat_c0.shape
     S = feat_c1.shape[1]
     f0, f1 = f32c(feat_c0), f32c(feat_c1)
     dev = f0.device
-    nws = lib.far_dual_softmax_match_workspace_bytes(N, Lq, S)
-    ws = torch.empty(nws, dtype=torch.uint8, device=dev)  # private: must survive until _gather
-    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-    conf = torch.empty((N, Lq, S), dtype=torch.float32, device=dev) if return_conf_matrix else None
+    h = _MatchHandle()
+    h.nws = lib.far_dual_softmax_match_workspace_bytes(N, Lq, S)
+    h.ws = torch.empty(h.nws, dtype=torch.uint8, device=dev)  # private: must survive until _gather
+    h.cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    h.conf = torch.empty((N, Lq, S), dtype=torch.float32, device=dev) if return_conf_matrix else None
+    h.shape, h.hw, h.scales, h.dev = (N, Lq, S), (hw0_c, hw1_c), (float(scale0), float(scale1)), dev
     with _timed("far_dual_softmax_match_select"):
         check(lib.far_dual_softmax_match_select(ptr(f0), ptr(f1), N, Lq, S, C, float(temperature), float(thr),
-                                              int(border_rm), hw0_c[0], hw0_c[1], hw1_c[0], hw1_c[1], ptr(conf),
-                                              ptr(cnt), engine, ptr(ws), nws, stream()), "far_dual_softmax_match_select")
-    M = int(cnt.item())  # the reference's sync point
+                                              int(border_rm), hw0_c[0], hw0_c[1], hw1_c[0], hw1_c[1], ptr(h.conf),
+                                              ptr(h.cnt), engine, ptr(h.ws), h.nws, stream()), "far_dual_softmax_match_select")
+    cur = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    h.cnt_host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        h.cnt_host.copy_(h.cnt, non_blocking=True)
+        h.event = torch.cuda.Event()
+        h.event.record(side)
+    h.cnt.record_stream(side)
+    return h
+
+
+def dual_softmax_match_end(h):
+    """Second half (coarse_matching.py:193-263): waits for the match count only (not for the compute stream), then the
+    order-preserving compaction."""
+    lib = L.load()
+    h.event.synchronize()   # the reference's sync point, but only on the count's own copy
+    M = int(h.cnt_host[0])
+    N, Lq, S = h.shape
+    dev = h.dev
     b_ids = torch.empty(M, dtype=torch.int64, device=dev)
     i_ids = torch.empty(M, dtype=torch.int64, device=dev)
     j_ids = torch.empty(M, dtype=torch.int64, device=dev)
     mconf = torch.empty(M, dtype=torch.float32, device=dev)
     mk0 = torch.empty((M, 2), dtype=torch.float32, device=dev)
     mk1 = torch.empty((M, 2), dtype=torch.float32, device=dev)
-    check(lib.far_dual_softmax_match_gather(N, Lq, hw0_c[1], hw1_c[1], float(scale0), float(scale1), M, ptr(b_ids),
-                                            ptr(i_ids), ptr(j_ids), ptr(mconf), ptr(mk0), ptr(mk1), ptr(ws), nws,
+    check(lib.far_dual_softmax_match_gather(N, Lq, h.hw[0][1], h.hw[1][1], h.scales[0], h.scales[1], M, ptr(b_ids),
+                                            ptr(i_ids), ptr(j_ids), ptr(mconf), ptr(mk0), ptr(mk1), ptr(h.ws), h.nws,
                                             stream()), "far_dual_softmax_match_gather")
     out = {"b_ids": b_ids, "i_ids": i_ids, "j_ids": j_ids, "mconf": mconf, "mkpts0_c": mk0, "mkpts1_c": mk1}
-    if return_conf_matrix:
-        out["conf_matrix"] = conf
+    if h.conf is not None:
+        out["conf_matrix"] = h.conf
     return out
+
+
+def dual_softmax_match(feat_c0, feat_c1, hw0_c, hw1_c, thr, border_rm, temperature, scale0, scale1,
+                       return_conf_matrix=False, engine=L.ENGINE_AUTO):
+    """CoarseMatching.forward + get_coarse_match (coarse_matching.py:86-265), dual-softmax, eval.
+    Returns dict(b_ids,i_ids,j_ids,mconf,mkpts0_c,mkpts1_c[,conf_matrix]).  One device->host read of M, as in the
+    reference's torch.where (:193)."""
+    return dual_softmax_match_end(dual_softmax_match_begin(feat_c0, feat_c1, hw0_c, hw1_c, thr, border_rm, temperature,
+                                                           scale0, scale1, return_conf_matrix, engine))
 
 
 def fine_preprocess(feat_f0, feat_f1, feat_c0, feat_c1, b_ids, i_ids, j_ids, W, stride, w0c, w1c, down_w, down_b,

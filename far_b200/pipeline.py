@@ -24,8 +24,9 @@ from .loftr.pose import pose_mean_6d, pose_std_6d, rotation_6d_to_matrix
 
 class FarPosePipeline:
     def __init__(self, model, K0, K1, fine_pred_steps=None, prior_ransac=True, ransac_kwargs=None,
-                 first_solver='ransac'):
+                 first_solver='ransac', overlap=True):
         self.model = model
+        self.overlap = overlap
         self.K0, self.K1 = K0, K1
         self.steps = fine_pred_steps if fine_pred_steps is not None else model.config.get('fine_pred_steps', 1)
         # prior_ransac=True: the solver call between the two head invocations is the prior-guided RANSAC round of the
@@ -48,7 +49,14 @@ class FarPosePipeline:
         loftr_rt [N,3,4], num_matches [N] (before RANSAC), num_inliers [N] (after RANSAC), gating [N,2]."""
         m = self.model
         data = {'image0': image0, 'image1': image1}
-        m(data)
+        m.forward_feature_extraction(data)
+        handle = m.forward_coarse(data)
+        # The head trunk needs only the coarse features: queued BEFORE the host waits for the match count, so the GPU
+        # stays busy across the reference's torch.where sync and while the host issues the many small fine-level /
+        # solver launches.  Same ops, same results, different issue order.
+        if self.overlap and m.config.get('regress_rt') and m.config['regress'].get('reuse_trunk', True):
+            m.head_trunk(data)
+        m.forward_fine(data, handle)
         N = image0.shape[0]
         K0 = self.K0[:N] if self.K0.shape[0] >= N else self.K0.expand(N, 3, 3)
         K1 = self.K1[:N] if self.K1.shape[0] >= N else self.K1.expand(N, 3, 3)

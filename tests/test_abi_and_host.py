@@ -99,3 +99,49 @@ def test_synth_is_deterministic_and_emm_pos_table():
     t = get_positional_encodings(1, 4800)[0]
     assert torch.allclose(t, O.emm_positional_encodings_mp3d(), atol=1e-6)
     assert t.shape == (4800, 6) and torch.all(t[:, 5] == 1)
+
+
+def test_mapfree_regression_model_contract():
+    """SURVEY.md 8(b) RegressionModel: constructor keywords of the reference, 540 state-dict keys / 66,249,761
+    parameters (the probe count of the reference model incl. the frozen upstream LoFTR), reference key prefixes."""
+    from far_b200.mapfree import RegressionModel
+    m = RegressionModel(use_loftr_preds=True, use_vanilla_transformer=True, use_prior=True, inference=True)
+    sd = m.state_dict()
+    assert len(sd) == 540 and sum(p.numel() for p in m.parameters()) == 66_249_761
+    for k in ("encoder.firstconv.weight", "encoder.encoder3.2.conv3.weight", "encoder.upconv4.conv1.conv.weight",
+              "encoder.outconv.normalize.running_var", "head.resblock1.shortcut.0.weight",
+              "transformer.layers.5.self_attn.in_proj_weight", "transformer.layers.0.linear1.weight",
+              "matcher.loftr_coarse.layers.7.mlp.2.weight", "pose_regressor.0.weight", "moe_predictor.0.weight"):
+        assert k in sd, k
+    assert tuple(sd["moe_predictor.0.weight"].shape) == (512, 27648 + 18 + 3)
+    assert tuple(sd["head.resblock1.conv1.weight"].shape) == (64, 67, 3, 3)
+    assert all(not p.requires_grad for p in m.matcher.parameters())
+
+
+def test_solver_shims_degenerate_inputs_need_no_gpu():
+    """The reference's return-by-value error behaviour (metrics.py:82-84, pose_solver.py:33-34): fewer than 5 keypoints
+    -> (None, 0, 0, 0) / identity, decided on the host before any kernel is involved."""
+    import numpy as np
+    from far_b200 import solver
+    k = torch.zeros(4, 2)
+    K = torch.eye(3)
+    assert solver.estimate_pose(k, k, K, K, 0.5) == (None, 0, 0, 0)
+    assert solver.estimate_pose(k[:0], k[:0], K, K, 0.5, solver='prior_ransac', priorRT=np.eye(4)[:3]) == (None, 0, 0, 0)
+    es = solver.EssentialMatrixSolver({"EMAT_RANSAC": {"PIX_THRESHOLD": 2.0, "CONFIDENCE": 0.9999}}, True)
+    (R, t, n), a, b = es.estimate_pose(np.zeros((3, 2)), np.zeros((3, 2)), {"K_color0": K[None], "K_color1": K[None]})
+    assert np.array_equal(R, np.eye(3)) and np.array_equal(t, np.zeros(3)) and (n, a, b) == (0, 0, 0)
+    with pytest.raises(NotImplementedError):
+        solver.RANSAC(model_type='homography')
+
+
+def test_bench_reference_arm_runs_every_workload_contract():
+    """`bench.py --impl reference` prints the contract's JSON line for a cheap workload (the CPU port, no GPU)."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload",
+                          "micro_4096x2048", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["config"]["workload"] == "micro_4096x2048" and line["scaling"] == "strong"

@@ -247,3 +247,18 @@ def test_mapfree_forward_with_gpu_ransac():
     R, t = m(data)
     assert torch.isfinite(R).all() and torch.equal(data["loftr_rt"].cpu(), torch.eye(3, 4).expand(2, 3, 4))
     assert float(data["inliers"].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("B,N,h,d", [(3, 576, 3, 64), (2, 108, 8, 32), (1, 77, 2, 64), (2, 130, 1, 32)])
+def test_flash_softmax_attention_vs_fp64(B, N, h, d):
+    """far_softmax_attention on the tcgen05 flash kernel (timm Attention of the 8pt-ViT blocks: N 576, 3 x 64,
+    vision_transformer.py:250-257; nn.MultiheadAttention of the map-free TransformerEncoder: 108 tokens, 8 x 32) and
+    ragged token counts, against softmax(q k^T * scale) v in fp64.  Scores reach |s * scale| ~ 30."""
+    g = O.rng(B * 1000 + N)
+    qkv = O.randn(g, B, N, 3 * h * d, scale=2.0)
+    scale = d ** -0.5
+    out = ops.softmax_attention(cu(qkv), h, scale).cpu()
+    x = qkv.double().reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(x[0] @ x[1].transpose(-2, -1) * scale, dim=-1) @ x[2]          # [B,h,N,d]
+    ref = att.transpose(1, 2).reshape(B, N, h * d)
+    assert_close(out, ref, 3e-5, 2e-5, f"softmax attention B{B} N{N} h{h} d{d}")
