@@ -142,7 +142,7 @@ class Mp3dLoftrFar(Workload):
         self.img = synth.synth_pair_images(self.units, seed=20240002 + rank)
         K = synth.mp3d_intrinsics(self.units).to(dev)
         self.pipe = FarPosePipeline(self.model, K, K, prior_ransac=not self.args.no_prior_ransac,
-                                    first_solver=self.args.first_solver)
+                                    first_solver=self.args.first_solver, graph=not self.args.no_graph)
         self.nmatch = None
 
     def host_inputs(self):
@@ -174,6 +174,9 @@ class Mp3dLoftrFar(Workload):
                               "--no-trunk-reuse re-evaluates it)" if not a.no_trunk_reuse else
                               "re-evaluated by each of the 2 head invocations",
                 "matches_per_pair": float(self.nmatch.float().mean()) if self.nmatch is not None else None,
+                "cuda_graph": ("segment 1 (backbone -> coarse transformer -> score kernels -> head trunk) replayed from one "
+                               "CUDA graph; the match-count read-back and the M-dependent fine level / solver / gate stay eager")
+                if self.pipe.graph else f"off ({self.pipe.graph_error or '--no-graph'})",
                 "parallelism": f"pairs sharded dp{world}",
                 "l2": "working set (inputs 79 MB + weights 204 MB + activations >> 126 MB L2): inputs larger than L2",
                 "backbone": "cuDNN conv with TF32 allowed (the reference's torch default); all other math fp32"}
@@ -783,6 +786,7 @@ def main():
     ap.add_argument("--no-prior-ransac", action="store_true",
                     help="mp3d_loftr_far: re-run the first solver between the two head invocations instead of the "
                          "prior-guided RANSAC round (far_b200/ransac.py, 2048 hypotheses per pair)")
+    ap.add_argument("--no-graph", action="store_true", help="mp3d_loftr_far: do not replay segment 1 from a CUDA graph")
     ap.add_argument("--no-trunk-reuse", action="store_true",
                     help="re-evaluate the FAR head trunk in both head invocations, literally as the reference does")
     args = ap.parse_args()

@@ -24,13 +24,18 @@ class FarError(RuntimeError):
 
 
 class EncoderLayerWeights(Structure):
-    _fields_ = [(n, c_void_p) for n in ("wq", "wk", "wv", "wmerge", "wmlp0", "wmlp2", "g1", "b1", "g2", "b2")]
+    _fields_ = [(n, c_void_p) for n in ("wq", "wk", "wv", "wmerge", "wmlp0", "wmlp2", "g1", "b1", "g2", "b2")] + \
+        [("eps1", c_float), ("eps2", c_float)] + \
+        [(n, c_void_p) for n in ("ps_wq", "ps_wkv", "ps_wmerge", "ps_wmlp0", "ps_wmlp2")]
 
 
 _P = c_void_p
 _SIGS = {
     "far_abi_version": (c_int, []),
     "far_launch_count": (ctypes.c_ulonglong, []),
+    "far_tc_set_cross16": (c_int, [c_int]),
+    "far_tc_weight_split_bytes": (c_size_t, [c_int, c_int]),
+    "far_tc_weight_split": (c_int, [_P, c_int, c_int, c_int, _P, c_size_t, _P]),
     "far_linear_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "far_linear": (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int,
                            c_int, _P, c_size_t, _P]),
@@ -112,8 +117,17 @@ def load():
     return lib
 
 
+_profiling = False
+
+
 def profile_enable(on):
+    global _profiling
     check(load().far_profile_enable(int(on)), "far_profile_enable")
+    _profiling = bool(on)
+
+
+def profiling_enabled():
+    return _profiling
 
 
 def profile_read():

@@ -7,13 +7,17 @@ namespace far {
 int linear_dispatch(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
                     const float* bias, float* y, int ldy, int M, int N, int act, int act_cols, int engine,
                     float* workspace, size_t workspace_bytes, cudaStream_t st);
+int linear_dispatch_ps(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
+                       const float* presplit, float* y, int ldy, int M, int N, int act, int act_cols, int engine,
+                       float* workspace, size_t workspace_bytes, cudaStream_t st);
 int linear_attention_dispatch(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out,
                               int ldo, int N, int L, int S, int H, int D, float eps, int applied, float* workspace,
                               size_t workspace_bytes, cudaStream_t st);
 size_t linear_attention_ws_bytes(int N, int S, int H, int D);
 int la_reduce_summed(const float* k, int ldk, const float* v, int ldv, int N, int S, int applied, float* workspace,
                      size_t workspace_bytes, const float** summed_out, cudaStream_t st);
-int la_fold_merge(const float* summed, const float* Wm, int N, int C, int S, float* bhi, float* blo, cudaStream_t st);
+int la_fold_merge(const float* summed, const float* Wm, int N, int C, int S, float* bhi, float* blo, bool cat,
+                  cudaStream_t st);
 
 static inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
@@ -66,6 +70,17 @@ extern "C" int far_loftr_encoder_layer(const float* x, const float* source, floa
   float* lw = reinterpret_cast<float*>(base + p.lin);
   const size_t lwb = p.lin_bytes;
   const int ML = N * L, MS = N * S, D = C / nhead;
+  const float eps1 = w->eps1 > 0.f ? w->eps1 : 1e-5f, eps2 = w->eps2 > 0.f ? w->eps2 : 1e-5f;   // nn.LayerNorm default
+  // cached operand splits (far_tc_weight_split): tf32 (hi, lo) form, only meaningful with tf32 cross terms
+  const bool ps_on = !tc::tc_cross16_on();
+  const float* ps_wq = ps_on ? w->ps_wq : nullptr;
+  const float* ps_wkv = ps_on ? w->ps_wkv : nullptr;
+  const float* ps_wmerge = ps_on ? w->ps_wmerge : nullptr;
+  const float* ps_wmlp0 = ps_on ? w->ps_wmlp0 : nullptr;
+  const float* ps_wmlp2 = ps_on ? w->ps_wmlp2 : nullptr;
+  auto ps_lo = [](const float* ps, size_t n, size_t k) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(ps) + ((n * k * 4 + 1023) & ~size_t(1023)));
+  };
   int rc;
   // ---- fused tensor-core schedule (coarse / regress layers: D = 32, 8 heads) ----------------------------------------
   //   [K' | V] = source [Wk; Wv]^T  (one GEMM, elu+1 on the K' half)      -> KV, Ksum  (la_reduce, fixed-order merge)
@@ -81,6 +96,7 @@ extern "C" int far_loftr_encoder_layer(const float* x, const float* source, floa
   if (fused) {
     TcLinearEx a{};
     a.x1 = source; a.ldx1 = C; a.K1 = C; a.W = w->wk; a.ldw = C; a.W2 = w->wv; a.N1 = C;
+    if (ps_wkv) { a.Whi = ps_wkv; a.Wlo = ps_lo(ps_wkv, 2 * C, C); }
     a.y = k; a.ldy = 2 * C; a.M = MS; a.N = 2 * C; a.act = FAR_ACT_ELU1; a.act_cols = C;
     a.workspace = lw; a.workspace_bytes = lwb;
     if ((rc = tc_linear_ex(a, st))) return rc;
@@ -89,30 +105,33 @@ extern "C" int far_loftr_encoder_layer(const float* x, const float* source, floa
     char* bnb = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(base + p.bn) + 1023) & ~uintptr_t(1023));
     float* bhi = reinterpret_cast<float*>(bnb);
     float* blo = reinterpret_cast<float*>(bnb + align_up((size_t)N * C * C * 4));
-    if ((rc = la_fold_merge(summed, w->wmerge, N, C, S, bhi, blo, st))) return rc;
+    const bool cat = tc::tc_cross16_on();   // the grouped `message` GEMM reads q in place (raw-A): cross16 operand form
+    if ((rc = la_fold_merge(summed, w->wmerge, N, C, S, bhi, blo, cat, st))) return rc;
     TcLinearEx b{};
     b.x1 = x; b.ldx1 = C; b.K1 = C; b.W = w->wq; b.ldw = C; b.y = q; b.ldy = C; b.M = ML; b.N = C;
+    if (ps_wq) { b.Whi = ps_wq; b.Wlo = ps_lo(ps_wq, C, C); }
     b.act = FAR_ACT_ELU1; b.act_cols = -1; b.G = N; b.L = L;
     b.ksum = summed; b.ksum_rec = 32 * 32 + 32; b.ksum_off = 32 * 32; b.eps = 1e-6f;
     b.workspace = lw; b.workspace_bytes = lwb;
     if ((rc = tc_linear_ex(b, st))) return rc;
     TcLinearEx c{};
-    c.x1 = q; c.ldx1 = C; c.K1 = C; c.Whi = bhi; c.Wlo = blo; c.b_grouped = 1; c.y = msg; c.ldy = C; c.M = ML; c.N = C;
+    c.x1 = q; c.ldx1 = C; c.K1 = C; c.Whi = bhi; c.Wlo = blo; c.wlo_is_cat = cat ? 1 : 0; c.b_grouped = 1; c.y = msg; c.ldy = C; c.M = ML; c.N = C;
     c.act = FAR_ACT_NONE; c.act_cols = -1; c.G = N; c.L = L; c.workspace = lw; c.workspace_bytes = lwb;
     if ((rc = tc_linear_ex(c, st))) return rc;
-    if ((rc = far_layernorm(msg, w->g1, w->b1, nullptr, attn, ML, C, 1e-5f, stream))) return rc;  // attn := LN(msg)
-    if ((rc = linear_dispatch(x, C, C, attn, C, C, w->wmlp0, 2 * C, nullptr, hid, 2 * C, ML, 2 * C, FAR_ACT_RELU, -1, engine, lw, lwb, st))) return rc;
-    if ((rc = linear_dispatch(hid, 2 * C, 2 * C, nullptr, 0, 0, w->wmlp2, 2 * C, nullptr, msg, C, ML, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
-    return far_layernorm(msg, w->g2, w->b2, x, out, ML, C, 1e-5f, stream);
+    if ((rc = far_layernorm(msg, w->g1, w->b1, nullptr, attn, ML, C, eps1, stream))) return rc;  // attn := LN(msg)
+    if ((rc = linear_dispatch_ps(x, C, C, attn, C, C, w->wmlp0, 2 * C, ps_wmlp0, hid, 2 * C, ML, 2 * C, FAR_ACT_RELU, -1, engine, lw, lwb, st))) return rc;
+    if ((rc = linear_dispatch_ps(hid, 2 * C, 2 * C, nullptr, 0, 0, w->wmlp2, 2 * C, ps_wmlp2, msg, C, ML, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
+    return far_layernorm(msg, w->g2, w->b2, x, out, ML, C, eps2, stream);
   }
   // q/k projections with the elu(x)+1 feature map fused into the epilogue; v plain (:55-57, linear_attention.py:33-34)
-  if ((rc = linear_dispatch(x, C, C, nullptr, 0, 0, w->wq, C, nullptr, q, C, ML, C, FAR_ACT_ELU1, -1, engine, lw, lwb, st))) return rc;
+  if ((rc = linear_dispatch_ps(x, C, C, nullptr, 0, 0, w->wq, C, ps_wq, q, C, ML, C, FAR_ACT_ELU1, -1, engine, lw, lwb, st))) return rc;
   const bool kv_fused = !fuse_off && engine != 1 && (engine == 2 || tc_engine_default_on()) &&
                         tc_linear_supported(source, C, C, nullptr, 0, 0, w->wk, C, MS, 2 * C) && C % 32 == 0 &&
                         p.v == p.k + (size_t)MS * C * 4 && (long long)MS * 2 * C >= 128LL * 128 * 32;
   if (kv_fused) {  // [K' | V] = source [Wk; Wv]^T in one tensor-core GEMM (source read and split once)
     TcLinearEx a{};
     a.x1 = source; a.ldx1 = C; a.K1 = C; a.W = w->wk; a.ldw = C; a.W2 = w->wv; a.N1 = C;
+    if (ps_wkv) { a.Whi = ps_wkv; a.Wlo = ps_lo(ps_wkv, 2 * C, C); }
     a.y = k; a.ldy = 2 * C; a.M = MS; a.N = 2 * C; a.act = FAR_ACT_ELU1; a.act_cols = C;
     a.workspace = lw; a.workspace_bytes = lwb;
     if ((rc = tc_linear_ex(a, st))) return rc;
@@ -125,11 +144,11 @@ extern "C" int far_loftr_encoder_layer(const float* x, const float* source, floa
                                         workspace_bytes - p.la, st))) return rc;
   }
   // merge + norm1 (:58-59)
-  if ((rc = linear_dispatch(attn, C, C, nullptr, 0, 0, w->wmerge, C, nullptr, msg, C, ML, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
-  if ((rc = far_layernorm(msg, w->g1, w->b1, nullptr, attn, ML, C, 1e-5f, stream))) return rc;  // attn := LN(msg)
+  if ((rc = linear_dispatch_ps(attn, C, C, nullptr, 0, 0, w->wmerge, C, ps_wmerge, msg, C, ML, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
+  if ((rc = far_layernorm(msg, w->g1, w->b1, nullptr, attn, ML, C, eps1, stream))) return rc;  // attn := LN(msg)
   // mlp([x | message]) (:62-63): two K-segments instead of a materialised concat
-  if ((rc = linear_dispatch(x, C, C, attn, C, C, w->wmlp0, 2 * C, nullptr, hid, 2 * C, ML, 2 * C, FAR_ACT_RELU, -1, engine, lw, lwb, st))) return rc;
-  if ((rc = linear_dispatch(hid, 2 * C, 2 * C, nullptr, 0, 0, w->wmlp2, 2 * C, nullptr, msg, C, ML, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
+  if ((rc = linear_dispatch_ps(x, C, C, attn, C, C, w->wmlp0, 2 * C, ps_wmlp0, hid, 2 * C, ML, 2 * C, FAR_ACT_RELU, -1, engine, lw, lwb, st))) return rc;
+  if ((rc = linear_dispatch_ps(hid, 2 * C, 2 * C, nullptr, 0, 0, w->wmlp2, 2 * C, ps_wmlp2, msg, C, ML, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
   // norm2 + residual (:64-66)
-  return far_layernorm(msg, w->g2, w->b2, x, out, ML, C, 1e-5f, stream);
+  return far_layernorm(msg, w->g2, w->b2, x, out, ML, C, eps2, stream);
 }

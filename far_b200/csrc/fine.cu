@@ -8,7 +8,8 @@ int linear_dispatch(const float* x1, int ldx1, int K1, const float* x2, int ldx2
                     float* workspace, size_t workspace_bytes, cudaStream_t st);
 int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
                        const float* bias, const float* rowbias, int rowbias_group, float* y, int ldy, int M, int N,
-                       int act, int act_cols, int engine, float* workspace, size_t workspace_bytes, cudaStream_t st);
+                       int act, int act_cols, int engine, float* workspace, size_t workspace_bytes, cudaStream_t st,
+                       const float* presplit = nullptr);
 
 // One warp per (side, match, window position): copies the Cf-channel vector of one fine pixel (zero outside the
 // map: F.unfold padding) into win[(side*M + m)*WW + ww][:].  Replaces F.unfold + index (:40-47): reads

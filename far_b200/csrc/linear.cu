@@ -339,7 +339,16 @@ __global__ void pose_blend_mp3d_kernel(const float* __restrict__ pred, const flo
 // Host-side dispatcher shared with the layer composition in encoder_layer.cu.
 int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
                        const float* bias, const float* rowbias, int rowbias_group, float* y, int ldy, int M, int N,
-                       int act, int act_cols, int engine, float* workspace, size_t workspace_bytes, cudaStream_t st);
+                       int act, int act_cols, int engine, float* workspace, size_t workspace_bytes, cudaStream_t st,
+                       const float* presplit = nullptr);
+
+// `presplit`: optional far_tc_weight_split output for W (used when the tcgen05 engine is chosen)
+int linear_dispatch_ps(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
+                       const float* presplit, float* y, int ldy, int M, int N, int act, int act_cols, int engine,
+                       float* workspace, size_t workspace_bytes, cudaStream_t st) {
+  return linear_dispatch_rb(x1, ldx1, K1, x2, ldx2, K2, W, ldw, nullptr, nullptr, 1, y, ldy, M, N, act, act_cols, engine,
+                            workspace, workspace_bytes, st, presplit);
+}
 
 int linear_dispatch(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
                     const float* bias, float* y, int ldy, int M, int N, int act, int act_cols, int engine,
@@ -352,7 +361,8 @@ int linear_dispatch(const float* x1, int ldx1, int K1, const float* x2, int ldx2
 // implemented by the CUDA-core engine.
 int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
                        const float* bias, const float* rowbias, int rowbias_group, float* y, int ldy, int M, int N,
-                       int act, int act_cols, int engine, float* workspace, size_t workspace_bytes, cudaStream_t st) {
+                       int act, int act_cols, int engine, float* workspace, size_t workspace_bytes, cudaStream_t st,
+                       const float* presplit) {
   if (M <= 0 || N <= 0) return FAR_OK;
   FAR_REQUIRE(x1 && W && y && K1 > 0 && ldx1 >= K1 && ldw >= K1 + K2 && ldy >= N);
   FAR_REQUIRE((x2 == nullptr) == (K2 == 0));
@@ -367,7 +377,7 @@ int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int l
   if (rb_ok && (engine == 2 || (engine == 0 && tc_ok && tc_ws_ok && tc_linear_preferred(M, N, K1 + K2) &&
                                 tc_engine_default_on()))) {
     return tc_linear(x1, ldx1, K1, x2, ldx2, K2, W, ldw, bias, rowbias, rowbias_group, y, ldy, M, N, act, act_cols,
-                     workspace, workspace_bytes, st);
+                     workspace, workspace_bytes, st, presplit);
   }
 
   LinearArgs p{x1, ldx1, K1, x2, ldx2, K2, W, ldw, bias, y, ldy, M, N, act, act_cols, nullptr, 1, K1, rowbias,
@@ -454,7 +464,7 @@ extern "C" int far_profile_read(int id, double* total_ms, unsigned long long* la
   return FAR_OK;
 }
 
-extern "C" int far_abi_version(void) { return 1; }
+extern "C" int far_abi_version(void) { return 2; }
 extern "C" unsigned long long far_launch_count(void) { return far::g_launch_count; }
 
 extern "C" size_t far_linear_workspace_bytes(int M, int N, int K) {

@@ -481,6 +481,7 @@ int la_reduce_summed(const float* k, int ldk, const float* v, int ldv, int N, in
 //   message[l, o] = sum_{h,e} (Z Q KV_h S)[l, h*32+e] Wm[o, h*32+e] = sum_{h,d} (Z Q)[l, h*32+d] * Bn[o, h*32+d],
 //   Bn[o, h*32+d] = S * sum_e KV[n,h,d,e] * Wm[o, h*32+e]      (one [C,C] matrix per batch element n)
 // written directly as the tf32 hi / lo operand pair of the tcgen05 engine.  grid (N, H), block C (thread = o).
+template <bool kCat>
 __global__ void __launch_bounds__(256) la_fold_merge_kernel(const float* __restrict__ summed, const float* __restrict__ Wm,
                                                             int C, float fS, float* __restrict__ bhi,
                                                             float* __restrict__ blo) {
@@ -499,21 +500,44 @@ __global__ void __launch_bounds__(256) la_fold_merge_kernel(const float* __restr
   }
   float* oh = bhi + ((size_t)n * C + o) * C + h * D;
   float* ol = blo + ((size_t)n * C + o) * C + h * D;
-#pragma unroll 4
-  for (int d = 0; d < D; ++d) {
-    float acc = 0.f;
+  if (kCat) {
+    // cross16 operand form (tc_common.cuh): oh = the fp32 values, ol = [32 x bf16(lo) | 32 x bf16(value)] for this 32-wide
+    // k-block (row o, columns h*32 .. h*32+31)
+    uint32_t* oc = reinterpret_cast<uint32_t*>(ol);
+#pragma unroll 2
+    for (int d = 0; d < D; d += 2) {
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int e = 0; e < D; ++e) acc = fmaf(KV[d][e], w[e], acc);
-    acc *= fS;
-    const float hi = __uint_as_float(__float_as_uint(acc) & 0xFFFFE000u);
-    oh[d] = hi;
-    ol[d] = acc - hi;
+      for (int e = 0; e < D; ++e) { a0 = fmaf(KV[d][e], w[e], a0); a1 = fmaf(KV[d + 1][e], w[e], a1); }
+      a0 *= fS; a1 *= fS;
+      oh[d] = a0; oh[d + 1] = a1;
+      const float l0 = a0 - __uint_as_float(__float_as_uint(a0) & 0xFFFFE000u);
+      const float l1 = a1 - __uint_as_float(__float_as_uint(a1) & 0xFFFFE000u);
+      uint32_t plo, phi;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(plo) : "f"(l1), "f"(l0));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(phi) : "f"(a1), "f"(a0));
+      oc[d >> 1] = plo;
+      oc[16 + (d >> 1)] = phi;
+    }
+  } else {
+#pragma unroll 4
+    for (int d = 0; d < D; ++d) {
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < D; ++e) acc = fmaf(KV[d][e], w[e], acc);
+      acc *= fS;
+      const float hi = __uint_as_float(__float_as_uint(acc) & 0xFFFFE000u);
+      oh[d] = hi;
+      ol[d] = acc - hi;
+    }
   }
 }
 
-int la_fold_merge(const float* summed, const float* Wm, int N, int C, int S, float* bhi, float* blo, cudaStream_t st) {
+int la_fold_merge(const float* summed, const float* Wm, int N, int C, int S, float* bhi, float* blo, bool cat,
+                  cudaStream_t st) {
   FAR_REQUIRE(summed && Wm && bhi && blo && C % 32 == 0 && C <= 256 && (reinterpret_cast<uintptr_t>(Wm) & 15u) == 0);
-  la_fold_merge_kernel<<<dim3(N, C / 32), 256, 0, st>>>(summed, Wm, C, (float)S, bhi, blo);
+  if (cat) la_fold_merge_kernel<true><<<dim3(N, C / 32), 256, 0, st>>>(summed, Wm, C, (float)S, bhi, blo);
+  else la_fold_merge_kernel<false><<<dim3(N, C / 32), 256, 0, st>>>(summed, Wm, C, (float)S, bhi, blo);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }

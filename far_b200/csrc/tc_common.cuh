@@ -110,6 +110,36 @@ constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)
 constexpr uint32_t kIdescTf32N2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 
+// ---- "cross16": the two 2^-11-times-smaller cross products  A_hi B_lo + A_lo B_hi  of the split-operand scheme only
+// need ~8 significant bits each (their sum is a 2^-11 correction to A_hi B_hi), so they run as ONE bf16 MMA over a
+// K-concatenated operand pair:  A_cat = [bf16(A) | bf16(A_lo)],  B_cat = [bf16(B_lo) | bf16(B)]  -- 64 bf16 = one 128-byte
+// SWIZZLE_128B row per 32-float k-block, so tile shapes, TMA boxes and descriptors are unchanged.  Per k-block: 4 tf32
+// MMAs (main) + 4 bf16 MMAs (cross, K = 16 each) = 512 tensor cycles and 64 KB of operand fetch, instead of 768 cycles
+// and 80 KB with tf32 cross terms.  Relative accuracy 2^-19 per product (bf16 round-to-nearest of the correction terms)
+// instead of 2^-21: held to the same 2e-5 + 1e-5 |ref| tolerance vs fp64 in tests/test_gpu_tcgen05.py.
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+// two floats -> packed bf16x2 (round to nearest even); e0 lands in the low half (lower address)
+__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+  return d;
+}
+__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// whether the raw-A GEMM path uses bf16 cross terms (env FAR_TC_CROSS=tf32 restores full 3xTF32)
+bool tc_cross16_on();
+// B operand of the cross16 scheme from row-major weights: hi = W (raw copy; kind::tf32 ignores the low 13 bits), cat =
+// per 32-float k-block [16 words: 32 x bf16(lo) | 16 words: 32 x bf16(W)].  K % 32 == 0.
+__global__ void split_cat_kernel(const float* __restrict__ W, int ld, int K, long long rows, float* __restrict__ hi,
+                                 uint32_t* __restrict__ cat);
+
 // x = hi + lo with hi = tf32-truncated x.  Handles the [x1 | x2] concatenation: dst row stride = K1 + K2.
 __global__ void split_tf32_kernel(const float* __restrict__ x1, int ld1, int K1, const float* __restrict__ x2, int ld2,
                                   int K2, long long rows, float* __restrict__ hi, float* __restrict__ lo);

@@ -5,7 +5,7 @@
 //        -> tcgen05.st back into TMEM (P never touches shared or global memory)
 //   T += P V'             tcgen05.mma with the A operand (P) read from TMEM, B = V'^T tiles (K-major) from smem
 // and finally  F_it = V'_i^T T  on the CUDA cores (70x70x128, < 5 % of the unit).
-// TMEM columns: S_main [0,64) S_cross [64,128) P_hi [128,192) P_lo [192,256) T_main [256,352) T_cross [352,448).
+// TMEM columns: S/P buffer b: main [128b, 128b+64) cross [128b+64, 128b+128); T_main [256,336) T_cross [352,432).
 #include "tc_common.cuh"
 #include "tc_emm.cuh"
 
@@ -13,16 +13,16 @@ namespace far {
 namespace tc {
 
 constexpr int EBJ = 64;                     // keys per j-tile
-constexpr int EDVP = 96;                    // padded d+6 (3 chunks of 32 for the MMA N dimension)
+constexpr int EDVP = 80;                    // d+6 = 70 padded to the MMA N granularity (16): TS MMA time scales with N
 constexpr int E_Q_BYTES = 4 * TILE_BYTES;   // Q: 2 k-blocks x (hi, lo) x [128 x 32 floats]
 constexpr int E_KT = EBJ * BK * 4;          // 8 KiB: one K box  [64 keys x 32 floats]
-constexpr int E_VT = EDVP * BK * 4;         // 12 KiB: one V'^T box [96 channels x 32 keys]
+constexpr int E_VT = EDVP * BK * 4;         // 10 KiB: one V'^T box [80 channels x 32 keys]
 constexpr int E_K_STAGE = 4 * E_KT;         // 2 k-blocks x (hi, lo)
 constexpr int E_V_STAGE = 4 * E_VT;
-constexpr int E_STAGE = E_K_STAGE + E_V_STAGE;  // 80 KiB
+constexpr int E_STAGE = E_K_STAGE + E_V_STAGE;  // 72 KiB
 constexpr int E_BAR_BYTES = 1024;
-constexpr size_t EMM_SMEM = 1024 + E_Q_BYTES + 2 * E_STAGE + E_BAR_BYTES;  // 231,424 B
-constexpr int ETP = 97;                     // pitch of the final-stage T / V' staging tiles
+constexpr size_t EMM_SMEM = 1024 + E_Q_BYTES + 2 * E_STAGE + E_BAR_BYTES;
+constexpr int ETP = EDVP + 1;               // pitch of the final-stage T / V' staging tiles
 
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -154,7 +154,7 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   const uint32_t tmem_base = *tmem_slot_ptr;
   // TMEM columns: S/P buffer b: main [128b, 128b+64) cross [128b+64, 128b+128) -- the softmax warps overwrite S with
   // P (hi over main, lo over cross) in place, so two buffers let S(jt+1) run on the tensor pipe while the softmax of
-  // tile jt and then T += P V'(jt) proceed; T_main [256,352), T_cross [352,448).
+  // tile jt and then T += P V'(jt) proceed; T_main [256,336), T_cross [352,432).
   auto tSP = [&](int b) { return tmem_base + (uint32_t)(b * 128); };
   const uint32_t tT_main = tmem_base + 256, tT_cross = tmem_base + 352;
 
@@ -328,12 +328,13 @@ tc_emm_pv_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     mbar_wait(t_full, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = cgp; c < EDVP / 32; c += E_SM_WARPS / 4) {
-      uint32_t a[32], b[32];
-      tmem_ld32(tT_main + lane_off + (uint32_t)(c * 32), a);
-      tmem_ld32(tT_cross + lane_off + (uint32_t)(c * 32), b);
+    for (int c = cgp; c < EDVP / 16; c += E_SM_WARPS / 4) {
+      uint32_t a[16], b[16];
+      tmem_ld16_nw(tT_main + lane_off + (uint32_t)(c * 16), a);
+      tmem_ld16_nw(tT_cross + lane_off + (uint32_t)(c * 16), b);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int e = 0; e < 32; ++e) Ts[row][c * 32 + e] = __uint_as_float(a[e]) + __uint_as_float(b[e]);
+      for (int e = 0; e < 16; ++e) Ts[row][c * 16 + e] = __uint_as_float(a[e]) + __uint_as_float(b[e]);
     }
     {
       const int b = g / p.H, h = g % p.H, dv = p.d + 6;
@@ -378,7 +379,7 @@ __global__ void emm_vt_kernel(const float* __restrict__ v, long long sb, long lo
   const int b = g / H, h = g % H;
   const float* vb = v + (size_t)b * sb + (size_t)h * sh;
   const float* pb = pos + (size_t)(Bpos == 1 ? 0 : b) * N * 6;
-  for (int cc = 0; cc < EDVP / 32; ++cc) {
+  for (int cc = 0; cc < (EDVP + 31) / 32; ++cc) {
     for (int r = threadIdx.y; r < 32; r += 8) {  // r: token, threadIdx.x: channel (contiguous in v)
       const int tok = t0 + r, c = cc * 32 + threadIdx.x;
       float val = 0.f;
@@ -391,7 +392,7 @@ __global__ void emm_vt_kernel(const float* __restrict__ v, long long sb, long lo
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8) {  // r: channel, threadIdx.x: token (contiguous in the output)
       const int c = cc * 32 + r, tok = t0 + threadIdx.x;
-      if (tok < Npad) {
+      if (tok < Npad && c < EDVP) {
         const float val = tile[threadIdx.x][r];
         const float hh = __uint_as_float(__float_as_uint(val) & 0xFFFFE000u);
         const size_t o = ((size_t)g * EDVP + c) * Npad + tok;

@@ -42,6 +42,7 @@ struct GemmArgs {
   int kb1;          // raw-A: number of 32-wide k-blocks that come from x1 (= K1 / 32)
   const float* ksum; int ksum_rec, ksum_off, heads; float eps;  // ACT_ELU1Z: Ksum[(g*heads + h)*ksum_rec + ksum_off + d]
   const float* rowbias; int rb_group;  // + rowbias[(row / rb_group) * N + col]  (fine_preprocess: per-match coarse term)
+  int cross16;      // raw-A only: slot 1 = A_cat, slot 3 = B_cat, cross terms as bf16 MMAs (tc_common.cuh)
   int dbg;          // diagnostics (env FAR_TC_DBG): 1 = skip global stores, 2 = skip the epilogue body, 4 = skip MMAs
 };
 
@@ -201,13 +202,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             const uint64_t dAlo = make_kmajor_sw128_desc(sbase + 1 * TILE_BYTES);
             const uint64_t dBhi = make_kmajor_sw128_desc(sbase + 2 * TILE_BYTES);
             const uint64_t dBlo = make_kmajor_sw128_desc(sbase + 3 * TILE_BYTES);
+            if (kRawA && p.cross16) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              if (p.dbg & 4) break;
-              const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128-byte swizzle row
-              umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32N2, (kb | k) ? 1u : 0u);  // [main|cross] += Ahi [Bhi;Blo]
-              umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, 1u);                    // cross += Alo Bhi
-              (void)dBlo;
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                if (p.dbg & 4) break;
+                const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // 32 bytes per step: 8 tf32 or 16 bf16 of K
+                umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32, (kb | k) ? 1u : 0u);   // main  += A B      (tf32)
+                umma_bf16(tmem_small, dAlo + koff, dBlo + koff, kIdescBf16, (kb | k) ? 1u : 0u);  // cross += A_cat B_cat^T (bf16)
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                if (p.dbg & 4) break;
+                const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128-byte swizzle row
+                umma_tf32(tmem_main, dAhi + koff, dBhi + koff, kIdescTf32N2, (kb | k) ? 1u : 0u);  // [main|cross] += Ahi [Bhi;Blo]
+                umma_tf32(tmem_small, dAlo + koff, dBhi + koff, kIdescTf32, 1u);                    // cross += Alo Bhi
+              }
             }
             umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
             if (kb == kblocks - 1) umma_commit(tfull_bar(acc));  // accumulator complete
@@ -230,6 +240,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
           unsigned char* sa = smem_dyn + (base + stage * STAGE_BYTES - raw);
           float4* a4 = reinterpret_cast<float4*>(sa);
           float4* l4 = reinterpret_cast<float4*>(sa + TILE_BYTES);
+          if (p.cross16) {
+            // A_cat row r = [32 x bf16(x) | 32 x bf16(x - trunc_tf32(x))]: the fp32 chunk pair (2j, 2j+1) of a row becomes
+            // bf16 chunk j (hi half) and chunk 4+j (lo half); SWIZZLE_128B stores 16-byte chunk c of row r at c ^ (r & 7).
+            uint4* c4 = reinterpret_cast<uint4*>(sa + TILE_BYTES);
+#pragma unroll
+            for (int i = 0; i < ((p.dbg & 32) ? 0 : 4); ++i) {
+              const int q = ct + i * 128, r = q >> 2, j = q & 3, sw = r & 7;
+              const float4 u = a4[r * 8 + ((2 * j) ^ sw)], w = a4[r * 8 + ((2 * j + 1) ^ sw)];
+              uint4 hi, lo;
+              hi.x = pack_bf16x2(u.x, u.y); hi.y = pack_bf16x2(u.z, u.w); hi.z = pack_bf16x2(w.x, w.y); hi.w = pack_bf16x2(w.z, w.w);
+              lo.x = pack_bf16x2(tf32_lo(u.x), tf32_lo(u.y)); lo.y = pack_bf16x2(tf32_lo(u.z), tf32_lo(u.w));
+              lo.z = pack_bf16x2(tf32_lo(w.x), tf32_lo(w.y)); lo.w = pack_bf16x2(tf32_lo(w.z), tf32_lo(w.w));
+              c4[r * 8 + (j ^ sw)] = hi;
+              c4[r * 8 + ((4 + j) ^ sw)] = lo;
+            }
+          } else
 #pragma unroll
           for (int i = 0; i < ((p.dbg & 32) ? 0 : TILE_BYTES / 16 / 128); ++i) {  // dbg 32: skip the split itself
             const float4 v = a4[ct + i * 128];
@@ -382,6 +408,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
   }
 }
 
+__global__ void split_cat_kernel(const float* __restrict__ W, int ld, int K, long long rows, float* __restrict__ hi,
+                                 uint32_t* __restrict__ cat) {
+  const long long total = rows * K;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / K;
+    const int c = (int)(idx % K), w = c & 31, k0 = (c & ~31) + 2 * (w & 15);
+    const float* row = W + r * ld;
+    hi[idx] = row[c];
+    const float e0 = row[k0], e1 = row[k0 + 1];
+    cat[idx] = (w < 16) ? pack_bf16x2(tf32_lo(e0), tf32_lo(e1)) : pack_bf16x2(e0, e1);
+  }
+}
+
+static int g_cross16 = -1;
+bool tc_cross16_on() {
+  if (g_cross16 < 0) {
+    // default: full 3xTF32 (tf32 cross terms).  Measured on B200 (profiles/r2_cross16_ab.md): the bf16 cross terms cut
+    // the tensor cycles by a third but the kernel is paced by the shared-memory port, not the tensor pipe (245 vs 250 us
+    // per launch), so the 4x looser rounding buys nothing yet.  FAR_TC_CROSS=bf16 (or 1) / far_tc_set_cross16(1) enables.
+    const char* e = getenv("FAR_TC_CROSS");
+    g_cross16 = (e && (e[0] == 'b' || e[0] == '1')) ? 1 : 0;
+  }
+  return g_cross16 == 1;
+}
+int tc_cross16_set(int on) {
+  const int prev = tc_cross16_on() ? 1 : 0;
+  g_cross16 = on ? 1 : 0;
+  return prev;
+}
+
 // x = hi + lo with hi = tf32-truncated x.  Handles the [x1 | x2] concatenation: dst row stride = K1 + K2.
 __global__ void split_tf32_kernel(const float* __restrict__ x1, int ld1, int K1, const float* __restrict__ x2, int ld2,
                                   int K2, long long rows, float* __restrict__ hi, float* __restrict__ lo) {
@@ -503,15 +560,28 @@ int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
     split_tf32_kernel<<<sblocks, 256, 0, st>>>(a.x1, a.ldx1, a.K1, a.x2, a.ldx2, a.K2, M, xhi, xlo);
     FAR_CHECK_LAUNCH();
   }
+  // cross16 (tc_common.cuh): raw-A path with whole 32-float k-blocks; a pre-split B must then be in the (raw, cat) form
+  const bool cross16 = rawA && K % BK == 0 && (presplitB ? a.wlo_is_cat != 0 : tc_cross16_on());
+  if (presplitB && a.wlo_is_cat && !cross16) return FAR_ERR_ARG;
   if (!presplitB) {
     float* h = reinterpret_cast<float*>(wbase);
     float* l = reinterpret_cast<float*>(wbase + al((size_t)N * K * 4));
     const int N1 = a.W2 ? a.N1 : N;  // rows [0,N1) from W, rows [N1,N) from W2 (fused projections, e.g. [Wk; Wv])
-    split_tf32_kernel<<<sblocks, 256, 0, st>>>(a.W, a.ldw, K, nullptr, 0, 0, N1, h, l);
-    FAR_CHECK_LAUNCH();
-    if (a.W2) {
-      split_tf32_kernel<<<sblocks, 256, 0, st>>>(a.W2, a.ldw, K, nullptr, 0, 0, N - N1, h + (size_t)N1 * K, l + (size_t)N1 * K);
+    if (cross16) {
+      split_cat_kernel<<<sblocks, 256, 0, st>>>(a.W, a.ldw, K, N1, h, reinterpret_cast<uint32_t*>(l));
       FAR_CHECK_LAUNCH();
+      if (a.W2) {
+        split_cat_kernel<<<sblocks, 256, 0, st>>>(a.W2, a.ldw, K, N - N1, h + (size_t)N1 * K,
+                                                  reinterpret_cast<uint32_t*>(l) + (size_t)N1 * K);
+        FAR_CHECK_LAUNCH();
+      }
+    } else {
+      split_tf32_kernel<<<sblocks, 256, 0, st>>>(a.W, a.ldw, K, nullptr, 0, 0, N1, h, l);
+      FAR_CHECK_LAUNCH();
+      if (a.W2) {
+        split_tf32_kernel<<<sblocks, 256, 0, st>>>(a.W2, a.ldw, K, nullptr, 0, 0, N - N1, h + (size_t)N1 * K, l + (size_t)N1 * K);
+        FAR_CHECK_LAUNCH();
+      }
     }
     whi = h; wlo = l;
   }
@@ -548,6 +618,7 @@ int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
     p.rowbias = a.rowbias; p.rb_group = a.rowbias_group;
   }
   p.dbg = dbg;
+  p.cross16 = cross16 ? 1 : 0;
   const int tiles = G * ceil_div(L, BM) * ceil_div(N, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   ProfScope prof(PROF_TC_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)Gb * N * K + (double)M * N), st);
@@ -561,10 +632,14 @@ int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
 
 int tc_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
               const float* bias, const float* rowbias, int rowbias_group, float* y, int ldy, int M, int N, int act,
-              int act_cols, float* workspace, size_t workspace_bytes, cudaStream_t st) {
+              int act_cols, float* workspace, size_t workspace_bytes, cudaStream_t st, const float* presplit) {
   if (workspace == nullptr || workspace_bytes < tc_linear_workspace_need(x1, ldx1, K1, x2, ldx2, K2, M, N))
     return FAR_ERR_WORKSPACE;
   TcLinearEx a{};
+  if (presplit != nullptr) {   // far_tc_weight_split output: tf32 hi at 0, lo at al(N*K*4)
+    a.Whi = presplit;
+    a.Wlo = reinterpret_cast<const float*>(reinterpret_cast<const char*>(presplit) + tc::al((size_t)N * (K1 + K2) * 4));
+  }
   a.x1 = x1; a.ldx1 = ldx1; a.K1 = K1; a.x2 = x2; a.ldx2 = ldx2; a.K2 = K2;
   a.W = W; a.ldw = ldw; a.bias = bias; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.act = act; a.act_cols = act_cols;
   a.rowbias = rowbias; a.rowbias_group = rowbias_group;
@@ -573,3 +648,21 @@ int tc_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int 
 }
 
 }  // namespace far
+
+extern "C" int far_tc_set_cross16(int on) { return far::tc::tc_cross16_set(on); }
+
+// ---- cached weight operands: the static weights of a module are split once, not on every call (114 split launches per
+// 32-pair FAR step otherwise) ----------------------------------------------------------------------------------------------
+extern "C" size_t far_tc_weight_split_bytes(int N, int K) { return 2 * far::tc::al((size_t)N * K * 4) + 1024; }
+
+extern "C" int far_tc_weight_split(const float* W, int ldw, int N, int K, float* out, size_t out_bytes, void* stream) {
+  using namespace far;
+  using namespace far::tc;
+  FAR_REQUIRE(W && out && N > 0 && K > 0 && ldw >= K && (reinterpret_cast<uintptr_t>(out) & 1023u) == 0);
+  if (out_bytes < far_tc_weight_split_bytes(N, K)) return FAR_ERR_WORKSPACE;
+  float* hi = out;
+  float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(out) + al((size_t)N * K * 4));
+  split_tf32_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(W, ldw, K, nullptr, 0, 0, N, hi, lo);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}

@@ -9,12 +9,14 @@ bool tc_linear_supported(const float* x1, int ldx1, int K1, const float* x2, int
 bool tc_linear_preferred(int M, int N, int K);
 // whether engine=0 (auto) should pick the tensor-core engine (env FAR_TC=0 disables)
 bool tc_engine_default_on();
+// whether raw-A GEMMs run their cross terms as bf16 MMAs (tc_common.cuh "cross16"); FAR_TC_CROSS=tf32 disables
+namespace tc { bool tc_cross16_on(); }
 size_t tc_linear_workspace_bytes(int M, int N, int K);
 // exact need for these operands (no activation split buffers when TMA can read the activations in place)
 size_t tc_linear_workspace_need(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, int M, int N);
 int tc_linear(const float* x1, int ldx1, int K1, const float* x2, int ldx2, int K2, const float* W, int ldw,
               const float* bias, const float* rowbias, int rowbias_group, float* y, int ldy, int M, int N, int act,
-              int act_cols, float* workspace, size_t workspace_bytes, cudaStream_t st);
+              int act_cols, float* workspace, size_t workspace_bytes, cudaStream_t st, const float* presplit = nullptr);
 
 // Extended entry: fused weight blocks ([W; W2]), pre-split (and optionally per-group) B, grouped rows, and the
 // linear-attention normaliser fused into the elu+1 epilogue.
@@ -24,6 +26,7 @@ struct TcLinearEx {
   const float* W; int ldw;          // [N1 (or N), K] weights (ignored when Whi != nullptr)
   const float* W2; int N1;          // optional second block: rows [N1, N) come from W2 [N - N1, K]
   const float* Whi; const float* Wlo;  // pre-split B: [Gb][N][K] hi / lo (tf32-truncated / remainder)
+  int wlo_is_cat;                   // pre-split B in the cross16 form: Whi = raw fp32, Wlo = bf16 [lo | hi] per k-block (tc_common.cuh)
   int b_grouped;                    // B has one [N,K] matrix per group
   const float* bias;
   float* y; int ldy;

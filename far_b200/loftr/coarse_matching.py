@@ -26,7 +26,7 @@ class CoarseMatching(nn.Module):
         self.materialize_conf_matrix = bool(config.get('materialize_conf_matrix', False))
         self.engine = ENGINE_AUTO
 
-    def forward_begin(self, feat_c0, feat_c1, data, mask_c0=None, mask_c1=None):
+    def forward_begin(self, feat_c0, feat_c1, data, mask_c0=None, mask_c1=None, defer_readback=False):
         """Launch the score / decision kernels and the asynchronous read-back of the match count; returns a handle for
         forward_end().  GPU work queued in between overlaps the host's wait for M (ops.dual_softmax_match_begin)."""
         if mask_c0 is not None or 'mask0' in data:
@@ -38,7 +38,8 @@ class CoarseMatching(nn.Module):
             raise NotImplementedError("per-image scale0/scale1 (MegaDepth resize) is outside the FAR eval path")
         return ops.dual_softmax_match_begin(feat_c0, feat_c1, tuple(data['hw0_c']), tuple(data['hw1_c']), self.thr,
                                             self.border_rm, self.temperature, scale, scale,
-                                            return_conf_matrix=self.materialize_conf_matrix, engine=self.engine)
+                                            return_conf_matrix=self.materialize_conf_matrix, engine=self.engine,
+                                            defer_readback=defer_readback)
 
     def forward_end(self, handle, data):
         m = ops.dual_softmax_match_end(handle)

@@ -54,7 +54,7 @@ class LoFTR(nn.Module):
                      'feats_c': feats_c})
 
     # ------------------------------------------------------------------ 2-5. transformer + matching (CUDA kernels)
-    def forward_coarse(self, data):
+    def forward_coarse(self, data, defer_readback=False):
         """Positional encoding -> coarse LoFTR -> score / decision kernels of the coarse matcher.  Stops before the
         reference's host sync on the match count (coarse_matching.py:193): returns the handle forward_fine() completes,
         so a caller can queue work that only needs the coarse features (the FAR head trunk) in between."""
@@ -63,7 +63,7 @@ class LoFTR(nn.Module):
         feat_c0 = self.pos_encoding.forward_flatten(data['featmap0'])   # [N, HW, C]
         feat_c1 = self.pos_encoding.forward_flatten(data['featmap1'])
         feat_c0, feat_c1 = self.loftr_coarse(feat_c0, feat_c1)
-        handle = self.coarse_matching.forward_begin(feat_c0, feat_c1, data)
+        handle = self.coarse_matching.forward_begin(feat_c0, feat_c1, data, defer_readback=defer_readback)
         data.update({'featmap0': feat_c0, 'featmap1': feat_c1, 'mask_c0': None, 'mask_c1': None,
                      'translation_scale': None})
         return handle

@@ -52,6 +52,7 @@ class LoFTREncoderLayer(nn.Module):
         self.norm1 = nn.LayerNorm(d_model)
         self.norm2 = nn.LayerNorm(d_model)
         self.engine = ENGINE_AUTO
+        self.cache_weight_split = True
 
     def _weights(self):
         return {"q_proj": self.q_proj.weight, "k_proj": self.k_proj.weight, "v_proj": self.v_proj.weight,
@@ -59,11 +60,30 @@ class LoFTREncoderLayer(nn.Module):
                 "norm1_w": self.norm1.weight, "norm1_b": self.norm1.bias,
                 "norm2_w": self.norm2.weight, "norm2_b": self.norm2.bias}
 
+    def _presplit(self, device):
+        """tcgen05 operand splits of the five static weight blocks, cached on the module and refreshed when a weight's
+        version counter / storage changes (load_state_dict, .to(), an optimizer step).  Inference only: under autograd
+        or on the CPU nothing is cached."""
+        ws = (self.q_proj.weight, self.k_proj.weight, self.v_proj.weight, self.merge.weight, self.mlp[0].weight,
+              self.mlp[2].weight)
+        key = tuple((w.data_ptr(), w._version) for w in ws) + (str(device),)
+        c = getattr(self, "_far_presplit", None)
+        if c is None or c[0] != key:
+            with torch.no_grad():
+                kv = torch.cat([self.k_proj.weight, self.v_proj.weight], dim=0).contiguous()
+                c = (key, {"q_proj": ops.tc_weight_split(self.q_proj.weight), "kv": ops.tc_weight_split(kv),
+                           "merge": ops.tc_weight_split(self.merge.weight), "mlp0": ops.tc_weight_split(self.mlp[0].weight),
+                           "mlp2": ops.tc_weight_split(self.mlp[2].weight)})
+            self._far_presplit = c
+        return c[1]
+
     def forward(self, x, source, x_mask=None, source_mask=None, loftr_preds=None):
         """x [N,L,C], source [N,S,C] -> [N,L,C]   (transformer.py:44-67)."""
         if x_mask is not None or source_mask is not None:
             raise NotImplementedError("padding masks are outside the FAR eval path")
-        return ops.loftr_encoder_layer(x, source, self._weights(), self.nhead, self.engine)
+        ps = self._presplit(x.device) if (x.is_cuda and self.cache_weight_split and not torch.is_grad_enabled()) else None
+        return ops.loftr_encoder_layer(x, source, self._weights(), self.nhead, self.engine, self.norm1.eps,
+                                       self.norm2.eps, ps)
 
 
 class LocalFeatureTransformer(nn.Module):

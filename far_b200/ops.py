@@ -206,16 +206,42 @@ def linear_attention(q, k, v, eps=1e-6, feature_map_applied=False):
     return out
 
 
-def loftr_encoder_layer(x, source, weights, nhead, engine=L.ENGINE_AUTO):
+def tc_weight_split(weight):
+    """tcgen05 operand form (tf32 hi | lo) of a static [N,K] weight, computed once (far_tc_weight_split)."""
+    lib = L.load()
+    w = weight.detach()
+    if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 2):
+        raise L.FarError("tc_weight_split needs a contiguous fp32 CUDA [N,K] weight")
+    N, K = w.shape
+    nbytes = lib.far_tc_weight_split_bytes(N, K)
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=w.device)
+    off = (-buf.data_ptr()) % 1024
+    out = buf[off:off + nbytes]
+    check(lib.far_tc_weight_split(ptr(w), K, N, K, ptr(out), nbytes, stream()), "far_tc_weight_split")
+    return out
+
+
+_ENC_KEYS = ("q_proj", "k_proj", "v_proj", "merge", "mlp0", "mlp2", "norm1_w", "norm1_b", "norm2_w", "norm2_b")
+
+
+def loftr_encoder_layer(x, source, weights, nhead, engine=L.ENGINE_AUTO, eps1=1e-5, eps2=1e-5, presplit=None):
     """LoFTREncoderLayer.forward (transformer.py:44-67), masks None.  `weights`: dict with the layer's tensors
-    q_proj,k_proj,v_proj,merge,mlp0,mlp2,norm1_w,norm1_b,norm2_w,norm2_b (CUDA fp32 contiguous)."""
+    q_proj,k_proj,v_proj,merge,mlp0,mlp2,norm1_w,norm1_b,norm2_w,norm2_b (CUDA fp32 contiguous, on x's device --
+    checked: the C side reads raw pointers).  `presplit`: optional dict of tc_weight_split outputs for
+    q_proj, kv ([k_proj; v_proj] stacked), merge, mlp0, mlp2 (cached by the module)."""
     lib = L.load()
     N, Lq, C = x.shape
     S = source.shape[1]
     x_, s_ = f32c(x), f32c(source)
+    for k in _ENC_KEYS:
+        t = weights[k]
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == x_.device):
+            raise L.FarError(f"loftr_encoder_layer: weight '{k}' must be a contiguous fp32 CUDA tensor on {x_.device} "
+                             f"(got {t.dtype}, {t.device}, contiguous={t.is_contiguous()})")
     out = torch.empty_like(x_)
-    w = L.EncoderLayerWeights(*[ptr(weights[k]) for k in ("q_proj", "k_proj", "v_proj", "merge", "mlp0", "mlp2",
-                                                          "norm1_w", "norm1_b", "norm2_w", "norm2_b")])
+    ps = presplit or {}
+    w = L.EncoderLayerWeights(*[ptr(weights[k]) for k in _ENC_KEYS], float(eps1), float(eps2),
+                              *[ptr(ps.get(k)) for k in ("q_proj", "kv", "merge", "mlp0", "mlp2")])
     nws = lib.far_loftr_encoder_layer_workspace_bytes(N, Lq, S, C, nhead)
     ws = _ws(nws, x.device)
     with _timed("far_loftr_encoder_layer"):
@@ -240,7 +266,7 @@ def _side_stream(dev):
 
 
 def dual_softmax_match_begin(feat_c0, feat_c1, hw0_c, hw1_c, thr, border_rm, temperature, scale0, scale1,
-                             return_conf_matrix=False, engine=L.ENGINE_AUTO):
+                             return_conf_matrix=False, engine=L.ENGINE_AUTO, defer_readback=False):
     """First half of CoarseMatching (coarse_matching.py:86-193): launches the score / decision kernels and starts an
     asynchronous read-back of the match count on a side stream.  The caller may queue more GPU work (e.g. the FAR head
     trunk, which only needs the coarse features) before calling dual_softmax_match_end(): the host then learns M while
@@ -260,6 +286,16 @@ def dual_softmax_match_begin(feat_c0, feat_c1, hw0_c, hw1_c, thr, border_rm, tem
         check(lib.far_dual_softmax_match_select(ptr(f0), ptr(f1), N, Lq, S, C, float(temperature), float(thr),
                                               int(border_rm), hw0_c[0], hw0_c[1], hw1_c[0], hw1_c[1], ptr(h.conf),
                                               ptr(h.cnt), engine, ptr(h.ws), h.nws, stream()), "far_dual_softmax_match_select")
+    h.event = None
+    if not defer_readback:   # defer_readback: the caller captures this call in a CUDA graph and starts the copy after replay
+        match_count_readback(h)
+    return h
+
+
+def match_count_readback(h):
+    """Start the asynchronous device->host copy of the match count on the side stream (ordered after everything queued
+    on the current stream so far, i.e. after the select kernels)."""
+    dev = h.dev
     cur = torch.cuda.current_stream(dev)
     side = _side_stream(dev)
     ready = torch.cuda.Event()
@@ -271,13 +307,14 @@ def dual_softmax_match_begin(feat_c0, feat_c1, hw0_c, hw1_c, thr, border_rm, tem
         h.event = torch.cuda.Event()
         h.event.record(side)
     h.cnt.record_stream(side)
-    return h
 
 
 def dual_softmax_match_end(h):
     """Second half (coarse_matching.py:193-263): waits for the match count only (not for the compute stream), then the
     order-preserving compaction."""
     lib = L.load()
+    if h.event is None:
+        match_count_readback(h)
     h.event.synchronize()   # the reference's sync point, but only on the count's own copy
     M = int(h.cnt_host[0])
     N, Lq, S = h.shape

@@ -24,9 +24,14 @@ from .loftr.pose import pose_mean_6d, pose_std_6d, rotation_6d_to_matrix
 
 class FarPosePipeline:
     def __init__(self, model, K0, K1, fine_pred_steps=None, prior_ransac=True, ransac_kwargs=None,
-                 first_solver='ransac', overlap=True):
+                 first_solver='ransac', overlap=True, graph=False):
         self.model = model
         self.overlap = overlap
+        # graph=True: segment 1 replays from a CUDA graph (one per input shape).  Opt-in: its outputs (feature maps, the
+        # `data` entries it writes) are static buffers reused by the next call.
+        self.graph = graph
+        self.graph_error = None
+        self._graphs = {}
         self.K0, self.K1 = K0, K1
         self.steps = fine_pred_steps if fine_pred_steps is not None else model.config.get('fine_pred_steps', 1)
         # prior_ransac=True: the solver call between the two head invocations is the prior-guided RANSAC round of the
@@ -43,19 +48,70 @@ class FarPosePipeline:
             return estimate_pose_batched(data, K0, K1)
         return estimate_pose_ransac_batched(data, K0, K1, prior, **self.ransac_kwargs)
 
-    @torch.no_grad()
-    def __call__(self, image0, image1):
-        """image0/1: [N,1,H,W] fp32 CUDA in [0,1].  Returns dict: pose [N,3,4] fused (R|t), regressed_rt [N,9],
-        loftr_rt [N,3,4], num_matches [N] (before RANSAC), num_inliers [N] (after RANSAC), gating [N,2]."""
+    # ---- segment 1: everything before the host needs the match count --------------------------------------------------
+    def _segment1(self, data, defer_readback=False):
         m = self.model
-        data = {'image0': image0, 'image1': image1}
         m.forward_feature_extraction(data)
-        handle = m.forward_coarse(data)
+        handle = m.forward_coarse(data, defer_readback=defer_readback)
         # The head trunk needs only the coarse features: queued BEFORE the host waits for the match count, so the GPU
         # stays busy across the reference's torch.where sync and while the host issues the many small fine-level /
         # solver launches.  Same ops, same results, different issue order.
         if self.overlap and m.config.get('regress_rt') and m.config['regress'].get('reuse_trunk', True):
             m.head_trunk(data)
+        return handle
+
+    def _segment1_graphed(self, image0, image1):
+        """Segment 1 (backbone -> coarse transformer -> score / decision kernels -> head trunk: static shapes, ~85 % of
+        the step's launches) as one CUDA graph per input shape: captured once after two eager warm-up runs (cuDNN
+        autotuning, weight-split / table caches), replayed afterwards.  The tensors it produces live in the graph's
+        memory pool and are OVERWRITTEN by the next call with the same shape."""
+        key = (tuple(image0.shape), tuple(image1.shape), image0.device.index)
+        ent = self._graphs.get(key)
+        if ent is None:
+            s0, s1 = torch.empty_like(image0), torch.empty_like(image1)
+            s0.copy_(image0)
+            s1.copy_(image1)
+            side = torch.cuda.Stream(device=image0.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    h = self._segment1({'image0': s0, 'image1': s1}, defer_readback=True)
+                    del h
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            data = {'image0': s0, 'image1': s1}
+            try:
+                with torch.cuda.graph(g):
+                    handle = self._segment1(data, defer_readback=True)
+            except Exception as ex:   # an op that cannot be captured: stay eager, loudly
+                import warnings
+                warnings.warn(f"FarPosePipeline: CUDA-graph capture of segment 1 failed ({ex!r}); running eagerly")
+                self.graph, self.graph_error = False, repr(ex)
+                data = {'image0': image0, 'image1': image1}
+                return data, self._segment1(data)
+            ent = (g, s0, s1, data, handle)
+            self._graphs[key] = ent
+        else:
+            g, s0, s1, data, handle = ent
+            s0.copy_(image0)
+            s1.copy_(image1)
+        g.replay()                # (the capture itself does not execute anything)
+        # the handle object is reused by every replay: start THIS call's read-back of the match count now
+        from . import ops
+        ops.match_count_readback(handle)
+        return dict(data), handle
+
+    @torch.no_grad()
+    def __call__(self, image0, image1):
+        """image0/1: [N,1,H,W] fp32 CUDA in [0,1].  Returns dict: pose [N,3,4] fused (R|t), regressed_rt [N,9],
+        loftr_rt [N,3,4], num_matches [N] (before RANSAC), num_inliers [N] (after RANSAC), gating [N,2]."""
+        from . import ops, _lib
+        m = self.model
+        if self.graph and ops.timer is None and not _lib.profiling_enabled():
+            data, handle = self._segment1_graphed(image0, image1)
+        else:
+            data = {'image0': image0, 'image1': image1}
+            handle = self._segment1(data)
         m.forward_fine(data, handle)
         N = image0.shape[0]
         K0 = self.K0[:N] if self.K0.shape[0] >= N else self.K0.expand(N, 3, 3)

@@ -48,6 +48,14 @@ const char* far_profile_name(int id);
 int far_profile_enable(int on);
 int far_profile_read(int id, double* total_ms, unsigned long long* launches, double* flops, double* bytes);
 
+/* Precision mode of the tcgen05 GEMM engine's correction terms (returns the previous setting).  x = hi + lo per operand
+ * (hi = tf32); the product is hi*hi + (hi*lo + lo*hi).  on = 0 (default): all three products in tf32 (relative accuracy
+ * 2^-21 per product).  on = 1 (env FAR_TC_CROSS=bf16 at start-up): the two 2^-11-times-smaller cross products run as one
+ * bf16 MMA over K-concatenated operands (2^-19 per product, 2/3 of the tensor cycles; measured 2 % faster on B200 because
+ * the kernel is paced by the shared-memory port).  Either way the engine is held to 2e-5 + 1e-5 |ref| against fp64
+ * (tests/test_gpu_tcgen05.py); the score / EMM kernels always use tf32 cross terms. */
+int far_tc_set_cross16(int on);
+
 /* ---- nn.Linear family --------------------------------------------------------------------------------
  * y[M,N] = act( [x1 | x2] * W^T + bias ),  x1:[M,K1] (ld ldx1), x2:[M,K2] (ld ldx2, may be NULL with K2=0),
  * W:[N,K1+K2] (ld ldw), bias:[N] or NULL, act applied to columns < act_cols only (act_cols<0: all).
@@ -119,7 +127,17 @@ int far_linear_attention(const float* q, int ldq, const float* k, int ldk, const
 typedef struct {
   const float *wq, *wk, *wv, *wmerge, *wmlp0, *wmlp2;
   const float *g1, *b1, *g2, *b2;
+  /* ABI version 2 */
+  float eps1, eps2;   /* eps of norm1 / norm2 (<= 0: nn.LayerNorm's default 1e-5) */
+  /* Optional cached tcgen05 operands of the static weights: outputs of far_tc_weight_split for wq [C,C], the stacked
+   * [wk; wv] [2C,C], wmerge [C,C], wmlp0 [2C,2C], wmlp2 [C,2C]; NULL = split on every call.  The caller owns the buffers
+   * and must refresh them when the weights change. */
+  const float *ps_wq, *ps_wkv, *ps_wmerge, *ps_wmlp0, *ps_wmlp2;
 } far_encoder_layer_weights;
+/* tcgen05 operand form of a static weight matrix W [N,K] (row pitch ldw): tf32 hi | lo pair, computed once per weight
+ * instead of on every GEMM call.  out: 1024-byte aligned, far_tc_weight_split_bytes(N, K) bytes. */
+size_t far_tc_weight_split_bytes(int N, int K);
+int far_tc_weight_split(const float* W, int ldw, int N, int K, float* out, size_t out_bytes, void* stream);
 size_t far_loftr_encoder_layer_workspace_bytes(int N, int L, int S, int C, int nhead);
 int far_loftr_encoder_layer(const float* x, const float* source, float* out, int N, int L, int S, int C,
                             int nhead, const far_encoder_layer_weights* w, int engine, float* workspace,

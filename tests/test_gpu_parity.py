@@ -571,3 +571,28 @@ def test_stem_conv7x7s2_relu(n, h, w):
     out = ops.stem_conv7x7s2_relu(cu(x), cu(wt), cu(b))
     assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
     assert_close(out, ref, 2e-5, 1e-5, "stem conv")
+
+
+def test_pipeline_cuda_graph_equals_eager():
+    """FarPosePipeline(graph=True): segment 1 (backbone -> coarse transformer -> score kernels -> head trunk) replayed from
+    a CUDA graph must give the eager pipeline's results bit for bit (same kernels, same order, deterministic merges),
+    on the capture call, on a replay with NEW inputs, and after switching shapes."""
+    from far_b200.pipeline import FarPosePipeline
+    cfg = far_eval_cfg(0.0)
+    model = LoFTR(cfg)
+    _load(model, synth.synth_state_dict(model.state_dict(), 31))
+    K = cu(synth.mp3d_intrinsics(2))
+    eager = FarPosePipeline(model, K, K, graph=False)
+    graphed = FarPosePipeline(model, K, K, graph=True)
+    for seed, n in ((5, 2), (6, 2), (7, 1), (8, 2)):
+        img0, img1 = synth.synth_pair_images(n, seed=seed)
+        a = eager(cu(img0), cu(img1))
+        ref = {k: a[k].clone() for k in ("pose", "regressed_rt", "loftr_rt", "num_matches", "num_inliers", "gating")}
+        ids = [a["data"][k].clone() for k in ("b_ids", "i_ids", "j_ids")]
+        b = graphed(cu(img0), cu(img1))
+        assert graphed.graph, graphed.graph_error
+        for k, v in ref.items():
+            assert torch.equal(b[k], v), (seed, k, (b[k].float() - v.float()).abs().max())
+        for k, v in zip(("b_ids", "i_ids", "j_ids"), ids):
+            assert torch.equal(b["data"][k], v), (seed, k)
+    assert len(graphed._graphs) == 2

@@ -96,3 +96,41 @@ def test_fused_encoder_layer_schedule(N, L, S):
     assert_close(fused, ref, 5e-5, 1e-5, "fused schedule vs fp64 oracle")
     assert_close(per_op, ref, 5e-5, 1e-5, "per-op schedule vs fp64 oracle")
     assert (fused - per_op).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("cross16", [1, 0])
+def test_tc_linear_cross_term_modes(cross16):
+    """far_tc_set_cross16: bf16 cross terms (default; 2/3 of the tensor cycles) vs all-tf32 cross terms.  Both must meet
+    the engine's fp32-level bar against fp64, on well-scaled, two-segment and adversarial mixed-magnitude operands; the
+    measured error statistics are printed (pytest -s) for profiles/."""
+    from far_b200 import _lib
+    lib = _lib.load()
+    prev = lib.far_tc_set_cross16(cross16)
+    try:
+        g = O.rng(500)
+        for (M, N, K) in ((4800, 512, 512), (9600, 256, 256), (2000, 768, 1024)):
+            x, w = O.randn(g, M, K, scale=1.5), O.randn(g, N, K, scale=K ** -0.5)
+            y = ops.linear(x.to(DEV), w.to(DEV), None, ACT_NONE, engine=ENGINE_TCGEN05).double().cpu()
+            ref = torch.nn.functional.linear(x.double(), w.double())
+            e = y - ref
+            print(f"cross16={cross16} {M}x{N}x{K}: max|err| {e.abs().max():.2e} rms {e.pow(2).mean().sqrt():.2e} "
+                  f"rms/|ref|rms {e.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt():.2e} "
+                  f"signed bias/|ref| {(e * torch.sign(ref)).mean() / ref.abs().mean():.2e}")
+            assert_close(y, ref, 2e-5, 1e-5, f"cross16={cross16} linear {M}x{N}x{K}")
+            assert e.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt() < 5e-6     # measured 0.9e-6 .. 2.7e-6 (tf32 cross terms)
+        x = O.randn(g, 1024, 256)
+        x[:, ::2] *= 1e3
+        x[:, 1::2] *= 1e-3
+        w = O.randn(g, 256, 256)
+        y = ops.linear(x.to(DEV), w.to(DEV), None, ACT_NONE, engine=ENGINE_TCGEN05)
+        ref = torch.nn.functional.linear(x.double(), w.double())
+        assert (y.double().cpu() - ref).abs().max().item() < 3e-6 * ref.abs().max().item()
+        # exact cancellation: y = x w^T - x w^T must stay at rounding level relative to the summands
+        xx = O.randn(g, 512, 256)
+        ww = O.randn(g, 128, 128)
+        wcat = torch.cat([ww, -ww], dim=1)
+        y0 = ops.linear(torch.cat([xx[:, :128], xx[:, :128]], 1).contiguous().to(DEV), wcat.to(DEV), None, ACT_NONE,
+                        engine=ENGINE_TCGEN05)
+        assert y0.abs().max().item() < 2e-5 * (xx[:, :128].abs().max() * ww.abs().max() * 128) ** 0.5 * 16
+    finally:
+        lib.far_tc_set_cross16(prev)

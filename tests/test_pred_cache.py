@@ -109,3 +109,43 @@ def test_ransac_host_glue_and_sampling_contract(golden_dir):
     top = np.argsort(-w)[: w.shape[0] // 10]
     assert abs(mass[top].sum() - w[top].sum() / w.sum()) < 0.05
     assert (O.ransac_sample_indices(np.ones(5), 4, seed=3) == -1).all()
+
+
+def test_mapfree_submission_writer(tmp_path):
+    """far_b200.submission against the reference's format (mapfree_6dreg/submission.py:30-82): quaternion w >= 0 that
+    reproduces the Gram-Schmidt rotation of the 6-D output, 6-decimal floats, int inliers / '0.0' fallback, NaN poses
+    skipped, one file per scene in the zip, no trailing newline."""
+    import zipfile
+    from far_b200.submission import SubmissionWriter, matrix_to_quaternion_wxyz
+    from far_b200.mapfree import rotation_6d_to_matrix
+    g = np.random.default_rng(12)
+    R6 = torch.from_numpy(g.standard_normal((5, 6)))
+    t = torch.from_numpy(g.standard_normal((5, 3)))
+    t[3, 1] = float("nan")
+    inl = torch.tensor([[120., 30., 2.], [0., 0., 0.], [7., 1., 0.], [5., 0., 0.], [999., 9., 9.]])
+    w = SubmissionWriter()
+    w.add_batch(["s1", "s1", "s2", "s2", "s1"], [f"seq1/frame_{i:05d}.jpg" for i in range(5)], R6, t, inl)
+    path = w.write(str(tmp_path / "sub.zip"))
+    with zipfile.ZipFile(path) as z:
+        assert sorted(z.namelist()) == ["pose_s1.txt", "pose_s2.txt"]
+        s1 = z.read("pose_s1.txt").decode()
+        s2 = z.read("pose_s2.txt").decode()
+    assert not s1.endswith("\n") and len(s1.split("\n")) == 3 and len(s2.split("\n")) == 1     # frame 3 (NaN) skipped
+    R = rotation_6d_to_matrix(R6)
+    for line, i in zip(s1.split("\n") + s2.split("\n"), (0, 1, 4, 2)):
+        f = line.split(" ")
+        assert f[0] == f"seq1/frame_{i:05d}.jpg" and len(f) == 9
+        q = np.array([float(x) for x in f[1:5]])
+        assert q[0] >= 0 and abs(np.linalg.norm(q) - 1) < 1e-5 and all(len(x.split(".")[1]) == 6 for x in f[1:8])
+        qw, qx, qy, qz = q
+        Rq = np.array([[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)],
+                       [2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)],
+                       [2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)]])
+        assert np.abs(Rq - R[i].numpy()).max() < 1e-5
+        assert np.abs(np.array([float(x) for x in f[5:8]]) - t[i].numpy()).max() < 1e-6
+        assert f[8] == ("0.0" if i == 1 else str(int(inl[i, 0])))
+    # the quaternion routine on the four branch cases (trace > 0 and each diagonal dominant)
+    Rs = torch.stack([torch.eye(3), torch.diag(torch.tensor([1., -1, -1])), torch.diag(torch.tensor([-1., 1, -1])),
+                      torch.diag(torch.tensor([-1., -1, 1]))]).double()
+    q = matrix_to_quaternion_wxyz(Rs)
+    assert torch.allclose(q.abs(), torch.eye(4, dtype=torch.float64), atol=1e-12)
