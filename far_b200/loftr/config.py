@@ -48,3 +48,34 @@ def upstream_loftr_cfg():
 
 def clone(cfg):
     return copy.deepcopy(cfg)
+
+
+class Cfg(dict):
+    """Attribute-access dict with the layout of the reference's yacs node (upper-case keys): what `PL_LoFTR(config)`
+    and `spvs_RT(data, config)` read (lightning_loftr.py:31-84, supervision.py:191-203)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _upper(d):
+    return Cfg({k.upper(): (_upper(v) if isinstance(v, dict) else v) for k, v in d.items()})
+
+
+def full_cfg(thr=0.2, coarse_layers=3, regress_layers=1):
+    """The full eval config of the FAR-LoFTR recipe of record (mp3d_loftr/scripts/eval_matterport.sh over
+    src/config/default.py, the keys the eval path reads): config.LOFTR.* (= far_eval_cfg, upper-cased), TRAINER.RANSAC_*,
+    the harness switches of test.py:162-223."""
+    c = Cfg()
+    c.LOFTR = _upper(far_eval_cfg(thr, coarse_layers, regress_layers))
+    c.TRAINER = Cfg({'RANSAC_PIXEL_THR': 0.5, 'RANSAC_CONF': 0.99999, 'N_VAL_PAIRS_TO_PLOT': 32, 'WORLD_SIZE': 1})
+    c.update({'USE_CORRESPONDENCE_TRANSFORMER': False, 'USE_PRED_CORR': False, 'STRICT_FALSE': False, 'SAVE_PREDS': None,
+              'NO_SAVE_PREDS': False, 'NO_SAVE_NUMCORR': False, 'SAVE_HARD_CORRES': False, 'SAVE_CORR': False,
+              'EVAL_FIT_ONLY': False, 'PL_VERSION': '1.6.0', 'EVAL_SPLIT': 'test'})
+    return c

@@ -596,3 +596,38 @@ def test_pipeline_cuda_graph_equals_eager():
         for k, v in zip(("b_ids", "i_ids", "j_ids"), ids):
             assert torch.equal(b["data"][k], v), (seed, k)
     assert len(graphed._graphs) == 2
+
+
+def test_pl_loftr_test_step_flow(tmp_path):
+    """The reference's eval call sequence (PL_LoFTR.test_step, lightning_loftr.py:325-421) on the drop-in modules, batch 1
+    like the reference: LoFTR.forward -> compute_supervision_RT (estimate_pose shim) -> 2 x forward_rt_prediction with the
+    prior-guided solver round in between -> compute_pose_errors on the regressed pose -> prediction-cache files.  The
+    first head invocation must equal the batched device pipeline's on the same solver numbers."""
+    from far_b200.lightning import PL_LoFTR
+    from far_b200.loftr import full_cfg
+    from far_b200 import pred_cache
+    cfg = full_cfg(0.0)
+    cfg.SAVE_PREDS = str(tmp_path)
+    os.makedirs(os.path.join(str(tmp_path), "test", "loftr_preds"))
+    os.makedirs(os.path.join(str(tmp_path), "test", "loftr_num_correspondences"))
+    pl = PL_LoFTR(cfg, split="test")
+    _load(pl.matcher, synth.synth_state_dict(pl.matcher.state_dict(), 21))
+    img0, img1 = synth.synth_pair_images(1, seed=77)
+    T = torch.eye(4)[None].clone()
+    T[0, :3, 3] = torch.tensor([0.2, -0.1, 1.0])
+    batch = {"image0": cu(img0), "image1": cu(img1), "K0": cu(synth.mp3d_intrinsics(1).double()),
+             "K1": cu(synth.mp3d_intrinsics(1).double()), "T_0to1": T, "dataset_name": ["mp3d"],
+             "pair_names": [("a.png",), ("b.png",)], "pair_id": torch.tensor(17)}
+    b2 = pl.test_step(dict(batch), 0, skip_eval=True)        # the solver / head keys before compute_pose_errors resets them
+    assert tuple(b2["regressed_rt"].shape) == (1, 9) and b2["priorRT"].shape == (3, 4)
+    assert tuple(b2["loftr_rt"].shape) == (3, 4) and int(b2["num_correspondences_before_ransac"][0]) > 500
+    assert 0 <= int(b2["inliers_best_ultra_tight"][0]) <= int(b2["inliers_best_tight"][0]) <= int(b2["num_correspondences"][0])
+    ret = pl.test_step(batch, 0)
+    m = ret["metrics"]
+    assert m["identifiers"] == ["a.png#b.png"] and len(m["R_errs"]) == 1 and np.isfinite(m["R_errs"][0])
+    assert np.isfinite(m["t_errs"][0]) and tuple(m["pred_R"].shape) == (1, 3, 3) and m["successful_fits"] == [0]
+    assert torch.equal(batch["regressed_rt"], b2["regressed_rt"]), "deterministic: same seed, same samples, same pose"
+    R = m["pred_R"][0].double()
+    assert (R @ R.T - torch.eye(3, dtype=torch.float64)).abs().max() < 1e-5
+    lp, nc = pred_cache.load_prediction(str(tmp_path), "test", "17")
+    assert tuple(lp.shape) == (1, 4, 4) and int(nc[0]) == 0   # regressed-pose branch: no solver count list (metrics.py:231-236)
