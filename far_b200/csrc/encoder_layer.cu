@@ -18,6 +18,8 @@ int la_reduce_summed(const float* k, int ldk, const float* v, int ldv, int N, in
                      size_t workspace_bytes, const float** summed_out, cudaStream_t st);
 int la_fold_merge(const float* summed, const float* Wm, int N, int C, int S, float* bhi, float* blo, bool cat,
                   cudaStream_t st);
+int la_reduce_fold(const float* kv, int N, int S, const float* Wm, float* workspace, size_t workspace_bytes, float* bhi,
+                   float* blo, bool cat, const float** summed_out, cudaStream_t st);
 
 static inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
@@ -101,12 +103,17 @@ extern "C" int far_loftr_encoder_layer(const float* x, const float* source, floa
     a.workspace = lw; a.workspace_bytes = lwb;
     if ((rc = tc_linear_ex(a, st))) return rc;
     const float* summed = nullptr;
-    if ((rc = la_reduce_summed(k, 2 * C, k + C, 2 * C, N, S, 1, la, workspace_bytes - p.la, &summed, st))) return rc;
     char* bnb = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(base + p.bn) + 1023) & ~uintptr_t(1023));
     float* bhi = reinterpret_cast<float*>(bnb);
     float* blo = reinterpret_cast<float*>(bnb + align_up((size_t)N * C * C * 4));
     const bool cat = tc::tc_cross16_on();   // the grouped `message` GEMM reads q in place (raw-A): cross16 operand form
-    if ((rc = la_fold_merge(summed, w->wmerge, N, C, S, bhi, blo, cat, st))) return rc;
+    static const bool la_sync_env = getenv("FAR_LA_SYNC") != nullptr;   // A/B: the round-1 synchronous reduce + partial sum
+    if (la_sync_env) {
+      if ((rc = la_reduce_summed(k, 2 * C, k + C, 2 * C, N, S, 1, la, workspace_bytes - p.la, &summed, st))) return rc;
+      if ((rc = la_fold_merge(summed, w->wmerge, N, C, S, bhi, blo, cat, st))) return rc;
+    } else if ((rc = la_reduce_fold(k, N, S, w->wmerge, la, workspace_bytes - p.la, bhi, blo, cat, &summed, st))) {
+      return rc;
+    }
     TcLinearEx b{};
     b.x1 = x; b.ldx1 = C; b.K1 = C; b.W = w->wq; b.ldw = C; b.y = q; b.ldy = C; b.M = ML; b.N = C;
     if (ps_wq) { b.Whi = ps_wq; b.Wlo = ps_lo(ps_wq, C, C); }

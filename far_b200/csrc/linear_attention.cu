@@ -542,6 +542,169 @@ int la_fold_merge(const float* summed, const float* Wm, int N, int C, int S, flo
   return FAR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fused encoder-layer path (encoder_layer.cu): KV_h = sum_s K'_h[s]^T V_h[s] and Ksum_h = sum_s K'_h[s] straight from the
+// [K' | V] block the projection GEMM just wrote ([N][S][2C], K' already holds elu+1), WITHOUT the v/S ... *S round trip
+// of linear_attention.py:43-50 (it cancels in  Bn = S * (K'^T V / S) * Wm^T; the raw sum is the better-rounded value).
+// HBM-bound (2 KB per token): a 3-stage cp.async ring keeps two 32 KB tiles in flight per CTA while the third is
+// consumed; batch elements are walked in REVERSE order because the GEMM wrote them in forward order -- the tail of the
+// 315 MB block is still in the 126 MB L2.  Partial sums per (n, head, split) in the la_reduce layout; the split merge
+// happens inside la_fold_merge_splits_kernel (fixed order), so no separate partial-sum launch.
+constexpr int LR_T = 16;        // tokens per stage
+constexpr int LR_STAGES = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;   // src-size 0: zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+template <int H>
+__global__ void __launch_bounds__(32 * H) la_reduce_kv_async_kernel(const float* __restrict__ kv, int S, int chunk,
+                                                                    float* __restrict__ ws) {
+  constexpr int D = 32, C = H * D, NT = 32 * H, ROW = 2 * C, ROW4 = ROW / 4;
+  extern __shared__ __align__(16) float la_sm[];
+  const int n = gridDim.x - 1 - blockIdx.x, z = blockIdx.y, t = threadIdx.x, h = t >> 5, lane = t & 31;
+  const int dq = lane >> 3, eq = lane & 7;  // this lane: d in [8 dq, 8 dq + 8), e in [4 eq, 4 eq + 4)
+  const int s_beg = z * chunk, s_end = min(S, s_beg + chunk);
+  const int ntiles = (s_end - s_beg + LR_T - 1) / LR_T;
+  const float* base = kv + (size_t)n * S * ROW;
+  auto issue = [&](int tile) {
+    if (tile < ntiles) {
+      float* dst = la_sm + (size_t)(tile % LR_STAGES) * LR_T * ROW;
+      const int s0 = s_beg + tile * LR_T;
+#pragma unroll
+      for (int i = 0; i < LR_T * ROW4 / NT; ++i) {
+        const int idx = t + i * NT, r = idx / ROW4, c4 = idx % ROW4;
+        const bool ok = s0 + r < s_end;
+        cp_async16(dst + (size_t)r * ROW + c4 * 4, base + (size_t)(ok ? s0 + r : s_beg) * ROW + c4 * 4, ok);
+      }
+    }
+    cp_async_commit();
+  };
+  float acc[8][4];
+  float ksum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    ksum[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  }
+#pragma unroll
+  for (int st = 0; st < LR_STAGES - 1; ++st) issue(st);
+  for (int tile = 0; tile < ntiles; ++tile) {
+    cp_async_wait<LR_STAGES - 2>();
+    __syncthreads();                       // tile `tile` landed for every thread; slot (tile-1) % STAGES is free again
+    issue(tile + LR_STAGES - 1);
+    const float* sm = la_sm + (size_t)(tile % LR_STAGES) * LR_T * ROW;
+#pragma unroll 4
+    for (int r = 0; r < LR_T; ++r) {       // rows past s_end are zero-filled: they add nothing
+      const float4 k0 = *reinterpret_cast<const float4*>(&sm[r * ROW + h * D + dq * 8]);
+      const float4 k1 = *reinterpret_cast<const float4*>(&sm[r * ROW + h * D + dq * 8 + 4]);
+      const float4 v0 = *reinterpret_cast<const float4*>(&sm[r * ROW + C + h * D + eq * 4]);
+      const float kk[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+      const float vv[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ksum[i] += kk[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(kk[i], vv[j], acc[i][j]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  float* out = ws + ((size_t)(n * H + h) * gridDim.y + z) * (D * D + D);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    *reinterpret_cast<float4*>(&out[(dq * 8 + i) * D + eq * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if (eq == 0) out[D * D + dq * 8 + i] = ksum[i];
+  }
+}
+
+// Split merge (fixed order) + Bn = scale * KV_n W_merge^T as the tcgen05 operand pair, and the summed record
+// (KV | Ksum) for the q-projection epilogue's normaliser.  grid (N, H), block C (thread = o).
+template <bool kCat>
+__global__ void __launch_bounds__(256) la_fold_merge_splits_kernel(const float* __restrict__ parts, int splits,
+                                                                   const float* __restrict__ Wm, int C, float scale,
+                                                                   float* __restrict__ summed, float* __restrict__ bhi,
+                                                                   float* __restrict__ blo) {
+  constexpr int D = 32, REC = D * D + D;
+  __shared__ float KV[D][D + 1];
+  const int n = blockIdx.x, h = blockIdx.y, H = gridDim.y, o = threadIdx.x;
+  const float* src = parts + (size_t)(n * H + h) * splits * REC;
+  float* rec = summed + (size_t)(n * H + h) * REC;
+  for (int idx = threadIdx.x; idx < REC; idx += blockDim.x) {
+    float a = 0.f;
+    for (int zz = 0; zz < splits; ++zz) a += src[(size_t)zz * REC + idx];
+    rec[idx] = a;
+    if (idx < D * D) KV[idx / D][idx % D] = a;
+  }
+  __syncthreads();
+  if (o >= C) return;
+  float w[D];
+#pragma unroll
+  for (int e = 0; e < D; e += 4) {
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(Wm + (size_t)o * C + h * D + e));
+    w[e] = w4.x; w[e + 1] = w4.y; w[e + 2] = w4.z; w[e + 3] = w4.w;
+  }
+  float* oh = bhi + ((size_t)n * C + o) * C + h * D;
+  float* ol = blo + ((size_t)n * C + o) * C + h * D;
+  uint32_t* oc = reinterpret_cast<uint32_t*>(ol);
+#pragma unroll 2
+  for (int d = 0; d < D; d += 2) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < D; ++e) { a0 = fmaf(KV[d][e], w[e], a0); a1 = fmaf(KV[d + 1][e], w[e], a1); }
+    a0 *= scale; a1 *= scale;
+    const float h0 = __uint_as_float(__float_as_uint(a0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(a1) & 0xFFFFE000u);
+    if (kCat) {   // cross16 operand form (tc_common.cuh): raw fp32 | [32 x bf16(lo) | 32 x bf16(value)]
+      oh[d] = a0; oh[d + 1] = a1;
+      uint32_t plo, phi;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(plo) : "f"(a1 - h1), "f"(a0 - h0));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(phi) : "f"(a1), "f"(a0));
+      oc[d >> 1] = plo;
+      oc[16 + (d >> 1)] = phi;
+    } else {
+      oh[d] = h0; oh[d + 1] = h1;
+      ol[d] = a0 - h0; ol[d + 1] = a1 - h1;
+    }
+  }
+}
+
+// [K'|V] block -> (summed record, Bn operand pair) in two launches.  workspace: la_reduce partial layout.
+int la_reduce_fold(const float* kv, int N, int S, const float* Wm, float* workspace, size_t workspace_bytes, float* bhi,
+                   float* blo, bool cat, const float** summed_out, cudaStream_t st) {
+  constexpr int HH = 8, CC = HH * 32, REC = 32 * 32 + 32;
+  FAR_REQUIRE(kv && Wm && workspace && bhi && blo && ptr_al16(kv) && ptr_al16(Wm));
+  if (workspace_bytes < linear_attention_ws_bytes(N, S, HH, 32) - 256) return FAR_ERR_WORKSPACE;
+  // one wave of 2 resident CTAs per SM (96 KB of shared memory each)
+  int sp = (2 * kNumSMs) / N;
+  const int maxs = ceil_div(S, 4 * LR_T);
+  if (sp > maxs) sp = maxs;
+  if (sp < 1) sp = 1;
+  const int lim = la_splits_allheads(N, S) > la_splits(N, S, HH) ? la_splits_allheads(N, S) : la_splits(N, S, HH);
+  if (sp > lim) sp = lim;                  // the workspace is sized for at most `lim` partial records per (n, head)
+  const int chunk = ceil_div(ceil_div(S, sp), LR_T) * LR_T;
+  float* summed = workspace + (size_t)N * HH * sp * REC;
+  const size_t smem = (size_t)LR_STAGES * LR_T * 2 * CC * 4;
+  static bool attr[64] = {};
+  if (first_use_on_device(attr))
+    cudaFuncSetAttribute(la_reduce_kv_async_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    ProfScope prof(PROF_LA_REDUCE, 2.0 * N * S * CC * 32, 4.0 * 2.0 * N * S * CC, st);
+    la_reduce_kv_async_kernel<HH><<<dim3(N, sp), 32 * HH, smem, st>>>(kv, S, chunk, workspace);
+  }
+  FAR_CHECK_LAUNCH();
+  if (cat) la_fold_merge_splits_kernel<true><<<dim3(N, HH), 256, 0, st>>>(workspace, sp, Wm, CC, 1.f, summed, bhi, blo);
+  else la_fold_merge_splits_kernel<false><<<dim3(N, HH), 256, 0, st>>>(workspace, sp, Wm, CC, 1.f, summed, bhi, blo);
+  FAR_CHECK_LAUNCH();
+  *summed_out = summed;
+  return FAR_OK;
+}
+
 size_t linear_attention_ws_bytes(int N, int S, int H, int D) {
   const int a = la_splits(N, S, H), b = la_splits_allheads(N, S);
   return (size_t)N * H * ((a > b ? a : b) + 1) * (D * D + D) * sizeof(float) + 256;

@@ -416,13 +416,47 @@ tc_lse64_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constan
           for (int e = 0; e < 32; ++e)
             x[e] = (rvalid && col0 + e < p.S) ? (__uint_as_float(a[e]) + __uint_as_float(b[e])) * p.scale2 : -INFINITY;
         }
-        // ---- row statistics, online across key tiles (4 independent chains: 2 warps per scheduler need the ILP)
+        // ---- ONE exponential per score serves the row and the column statistics: E = 2^(x - R) with R the maximum of
+        // this warp's 32 x 32 chunk (warp shuffle reduce, no block barrier).  Any reference >= the data is a valid
+        // log-sum-exp shift; what a shared reference can lose is a term that underflows (ex2.approx.ftz flushes below
+        // 2^-126), so the shared path is taken only when the whole chunk lies within 100 binades of R (warp-uniform test;
+        // otherwise, and for ragged edge chunks with -inf padding, the exact per-row / per-column maxima below).
         float c0 = fmaxf(x[0], x[4]), c1 = fmaxf(x[1], x[5]), c2 = fmaxf(x[2], x[6]), c3 = fmaxf(x[3], x[7]);
+        float d0 = fminf(x[0], x[4]), d1 = fminf(x[1], x[5]), d2 = fminf(x[2], x[6]), d3 = fminf(x[3], x[7]);
 #pragma unroll
         for (int e = 8; e < 32; e += 4) {
           c0 = fmaxf(c0, x[e]); c1 = fmaxf(c1, x[e + 1]); c2 = fmaxf(c2, x[e + 2]); c3 = fmaxf(c3, x[e + 3]);
+          d0 = fminf(d0, x[e]); d1 = fminf(d1, x[e + 1]); d2 = fminf(d2, x[e + 2]); d3 = fminf(d3, x[e + 3]);
         }
-        const float m_new = fmaxf(m_run, fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)));
+        const float tmx = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
+        const float R = warp_max(tmx);
+        const float mn = -warp_max(-fminf(fminf(d0, d1), fminf(d2, d3)));
+        const int col = col0 + lane;
+        if (R - mn <= 100.f) {   // (false for NaN / -inf padding)
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            x[e] = ex2(x[e] - R); x[e + 1] = ex2(x[e + 1] - R); x[e + 2] = ex2(x[e + 2] - R); x[e + 3] = ex2(x[e + 3] - R);
+            a0 += x[e]; a1 += x[e + 1]; a2 += x[e + 2]; a3 += x[e + 3];
+          }
+          const float m_new = fmaxf(m_run, R);
+          s_run = s_run * ex2(m_run - m_new) + ((a0 + a1) + (a2 + a3)) * ex2(R - m_new);
+          m_run = m_new;
+          // column sums of this warp's 32 rows: warp-private transpose of the exponentials
+#pragma unroll
+          for (int e = 0; e < 32; ++e) scr[lane][e] = x[e];
+          __syncwarp();
+          a0 = a1 = a2 = a3 = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; r += 4) {
+            a0 += scr[r][lane]; a1 += scr[r + 1][lane]; a2 += scr[r + 2][lane]; a3 += scr[r + 3][lane];
+          }
+          if (col < p.S) p.colpart[((size_t)g * 4 * IT + 4 * it + quarter) * p.S + col] = make_float2(R, (a0 + a1) + (a2 + a3));
+          __syncwarp();   // the next chunk overwrites scr
+          continue;
+        }
+        // ---- exact path: row statistics, online across key tiles (4 independent chains)
+        const float m_new = fmaxf(m_run, tmx);
         if (m_new > -INFINITY) {
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
@@ -453,7 +487,6 @@ tc_lse64_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constan
           }
           cs = (a0 + a1) + (a2 + a3);
         }
-        const int col = col0 + lane;
         if (col < p.S) p.colpart[((size_t)g * 4 * IT + 4 * it + quarter) * p.S + col] = make_float2(cmx, cs);
         __syncwarp();   // the next chunk overwrites scr
       }

@@ -629,5 +629,12 @@ def test_pl_loftr_test_step_flow(tmp_path):
     assert torch.equal(batch["regressed_rt"], b2["regressed_rt"]), "deterministic: same seed, same samples, same pose"
     R = m["pred_R"][0].double()
     assert (R @ R.T - torch.eye(3, dtype=torch.float64)).abs().max() < 1e-5
+    # regressed-pose branch: compute_pose_errors leaves the solver count list empty (metrics.py:231-236), so like the
+    # reference only the pose file is written (lightning_loftr.py:356) and the reader, which needs both files, falls back
+    # to the identity (test_streetlearn_interiornet.py:250-267)
+    assert os.path.exists(os.path.join(str(tmp_path), "test", "loftr_preds", "17.pt"))
+    saved = torch.load(os.path.join(str(tmp_path), "test", "loftr_preds", "17.pt"))
+    assert tuple(saved.shape) == (3, 4) and saved.dtype == torch.float64
+    assert torch.allclose(saved[:, :3], m["pred_R"][0].double(), atol=1e-12)
     lp, nc = pred_cache.load_prediction(str(tmp_path), "test", "17")
-    assert tuple(lp.shape) == (1, 4, 4) and int(nc[0]) == 0   # regressed-pose branch: no solver count list (metrics.py:231-236)
+    assert tuple(lp.shape) == (1, 3, 4) and int(nc[0]) == 0
