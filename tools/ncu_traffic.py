@@ -8,7 +8,8 @@ import json
 import sys
 
 CLASSES = {"tc_gemm_kernel": "tc_gemm_kernel", "tc_score_kernel": ("tc_score_kernel", "tc_lse64_kernel"), "tc_emm_pv_kernel": "tc_emm_pv_kernel",
-           "la_reduce": "la_reduce_allheads_kernel", "la_apply": "la_apply_allheads_kernel", "la_small_kernel": "la_small",
+           "la_reduce": ("la_reduce_allheads_kernel", "la_reduce_kv_async_kernel"), "eightpt_kernels": "eightpt",
+           "solver": ("ransac_", "pose_select", "essential_to_cand"), "la_apply": "la_apply_allheads_kernel", "la_small_kernel": "la_small",
            "layernorm": "layernorm", "linear_simt_kernel": "linear_simt_kernel", "fpn_fuse": "stem_conv7x7s2",
            "fine_window_gather_kernel": "fine_window_gather_kernel", "fine_match_kernel": "fine_match_kernel"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6}

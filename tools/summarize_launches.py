@@ -32,6 +32,10 @@ def main():
     if "--last-step" in sys.argv:  # one steady-state step: between the last two input torch.cat launches
         marks = [i for i, r in enumerate(rows) if "CatArrayBatchedCopy" in r[1] and r[3].startswith("(4736")]
         rows = rows[marks[-2]:marks[-1]]
+    for a in sys.argv:   # --last-of=K: the last 1/K of the launches (bench.py runs K equal steps; other workloads)
+        if a.startswith("--last-of="):
+            k = int(a.split("=")[1])
+            rows = rows[len(rows) - len(rows) // k:]
     tot = sum(r[2] for r in rows)
     agg = defaultdict(lambda: [0, 0.0])
     for _, k, v, _g in rows:
