@@ -769,6 +769,104 @@ def ransac_sample_indices(weights, H, seed, pair=0, S=8):
     return out
 
 
+# --------------------------------------------------------------------------------------- 8f rank 2: 5-point minimal solver
+def _mul_deg_one(a, b):
+    """kornia 0.7.1 `solvers.multiply_deg_one_poly` (un-vendored; restated): product of two linear forms in (x, y, z, 1)
+    -> the 10 coefficients of [x^2, xy, xz, x, y^2, yz, y, z^2, z, 1].  a, b: [..., 4]."""
+    return np.stack([a[..., 0] * b[..., 0], a[..., 0] * b[..., 1] + a[..., 1] * b[..., 0],
+                     a[..., 0] * b[..., 2] + a[..., 2] * b[..., 0], a[..., 0] * b[..., 3] + a[..., 3] * b[..., 0],
+                     a[..., 1] * b[..., 1], a[..., 1] * b[..., 2] + a[..., 2] * b[..., 1],
+                     a[..., 1] * b[..., 3] + a[..., 3] * b[..., 1], a[..., 2] * b[..., 2],
+                     a[..., 2] * b[..., 3] + a[..., 3] * b[..., 2], a[..., 3] * b[..., 3]], -1)
+
+
+def _mul_deg_two_one(a, b):
+    """kornia 0.7.1 `solvers.multiply_deg_two_one_poly` (restated): degree-2 poly (10 coefficients, order above) times a
+    linear form -> 20 coefficients of [x^3, y^3, x^2y, xy^2, x^2z, x^2, y^2z, y^2, xyz, xy | xz^2, xz, x, yz^2, yz, y, z^3,
+    z^2, z, 1] -- Nister's ordering: the first ten monomials are eliminated, the last ten are (x, y, 1) x powers of z."""
+    return np.stack([
+        a[..., 0] * b[..., 0], a[..., 4] * b[..., 1], a[..., 0] * b[..., 1] + a[..., 1] * b[..., 0],
+        a[..., 1] * b[..., 1] + a[..., 4] * b[..., 0], a[..., 0] * b[..., 2] + a[..., 2] * b[..., 0],
+        a[..., 0] * b[..., 3] + a[..., 3] * b[..., 0], a[..., 4] * b[..., 2] + a[..., 5] * b[..., 1],
+        a[..., 4] * b[..., 3] + a[..., 6] * b[..., 1],
+        a[..., 1] * b[..., 2] + a[..., 2] * b[..., 1] + a[..., 5] * b[..., 0],
+        a[..., 1] * b[..., 3] + a[..., 3] * b[..., 1] + a[..., 6] * b[..., 0],
+        a[..., 2] * b[..., 2] + a[..., 7] * b[..., 0],
+        a[..., 2] * b[..., 3] + a[..., 3] * b[..., 2] + a[..., 8] * b[..., 0],
+        a[..., 3] * b[..., 3] + a[..., 9] * b[..., 0], a[..., 5] * b[..., 2] + a[..., 7] * b[..., 1],
+        a[..., 5] * b[..., 3] + a[..., 6] * b[..., 2] + a[..., 8] * b[..., 1],
+        a[..., 6] * b[..., 3] + a[..., 9] * b[..., 1], a[..., 7] * b[..., 2],
+        a[..., 7] * b[..., 3] + a[..., 8] * b[..., 2], a[..., 8] * b[..., 3] + a[..., 9] * b[..., 2],
+        a[..., 9] * b[..., 3]], -1)
+
+
+def five_point_constraints(null4):
+    """cv_geometry.py:901-945 of `run_5point_our_kornia`: E(x,y,z) = x N0 + y N1 + z N2 + N3 with the four null vectors
+    null4 [9, 4] (entry (i,j) of the 3x3 is vector index 3j+i, `fun(i,j)` :898-899) -> the [10, 20] coefficient matrix of
+    the nine cubic trace constraints  E E^T E - 1/2 tr(E E^T) E = 0  (rows 0-8) and det E = 0 (row 9)."""
+    def fun(i, j):
+        return null4[3 * j + i]
+    c = np.zeros((10, 20))
+    c[9] = (_mul_deg_two_one(_mul_deg_one(fun(0, 1), fun(1, 2)) - _mul_deg_one(fun(0, 2), fun(1, 1)), fun(2, 0))
+            + _mul_deg_two_one(_mul_deg_one(fun(0, 2), fun(1, 0)) - _mul_deg_one(fun(0, 0), fun(1, 2)), fun(2, 1))
+            + _mul_deg_two_one(_mul_deg_one(fun(0, 0), fun(1, 1)) - _mul_deg_one(fun(0, 1), fun(1, 0)), fun(2, 2)))
+    d = {}
+    for i in range(3):
+        for j in range(3):
+            d[(i, j)] = sum(_mul_deg_one(fun(i, k), fun(j, k)) for k in range(3))
+    tr = 0.5 * (d[(0, 0)] + d[(1, 1)] + d[(2, 2)])
+    for i in range(3):
+        d[(i, i)] = d[(i, i)] - tr
+    cnt = 0
+    for i in range(3):
+        for j in range(3):
+            c[cnt] = sum(_mul_deg_two_one(d[(i, k)], fun(k, j)) for k in range(3))
+            cnt += 1
+    return c
+
+
+def run_5point_nister(points1, points2):
+    """cv_geometry.py:861-1041 `run_5point_our_kornia` for ONE minimal sample (5 correspondences, unit weights), fp64:
+    null space of the 5 epipolar equations (the 4 smallest right-singular vectors of X^T X, :886-896), the 10 x 20
+    constraint matrix, Gauss-Jordan on the cubic monomials (:952-956), Nister's 3 x 3 polynomial matrix A(z) (:958-969),
+    det A(z) = a degree-10 polynomial in z (the reference expands it with `determinant_to_polynomial`, :23-551; here by
+    polynomial products: the same polynomial), its REAL roots (the reference keeps the real part of every companion-matrix
+    eigenvalue, :984: complex roots yield junk models that its scoring step discards), x and y from two rows of A (:1008)
+    and E = -x N0 - y N1 + z N2 + N3 normalised (:1018-1022), returned as p2^T E p1 = 0 matrices [n_real, 3, 3]."""
+    x1, y1 = points1[:, 0].astype(np.float64), points1[:, 1].astype(np.float64)
+    x2, y2 = points2[:, 0].astype(np.float64), points2[:, 1].astype(np.float64)
+    X = np.stack([x1 * x2, x1 * y2, x1, y1 * x2, y1 * y2, y1, x2, y2, np.ones_like(x1)], -1)
+    _, _, Vt = np.linalg.svd(X.T @ X)
+    null4 = Vt[-4:].T                                   # [9, 4] = V[:, -4:]
+    c = five_point_constraints(null4)
+    try:
+        B = np.linalg.solve(c[:, :10], c[:, 10:])
+    except np.linalg.LinAlgError:
+        return np.zeros((0, 3, 3))
+    A = np.zeros((3, 13))
+    for i in range(3):
+        A[i, 1:4] = B[4 + 2 * i, 0:3]
+        A[i, 0:3] -= B[5 + 2 * i, 0:3]
+        A[i, 5:8] = B[4 + 2 * i, 3:6]
+        A[i, 4:7] -= B[5 + 2 * i, 3:6]
+        A[i, 9:13] = B[4 + 2 * i, 6:10]
+        A[i, 8:12] -= B[5 + 2 * i, 6:10]
+    P = [[np.poly1d(A[i, 0:4]), np.poly1d(A[i, 4:8]), np.poly1d(A[i, 8:13])] for i in range(3)]
+    det = (P[0][0] * (P[1][1] * P[2][2] - P[1][2] * P[2][1]) - P[0][1] * (P[1][0] * P[2][2] - P[1][2] * P[2][0])
+           + P[0][2] * (P[1][0] * P[2][1] - P[1][1] * P[2][0]))
+    roots = np.roots(det.coeffs)
+    roots = np.sort(roots[np.abs(roots.imag) < 1e-9 * (1 + np.abs(roots.real))].real)
+    out = []
+    for z in roots:
+        Bs = np.array([[np.polyval(A[i, 0:4], z), np.polyval(A[i, 4:8], z)] for i in range(3)])
+        bs = np.array([np.polyval(A[i, 8:13], z) for i in range(3)])
+        xy = np.linalg.lstsq(Bs, bs, rcond=None)[0]
+        e = null4[:, 0] * (-xy[0]) + null4[:, 1] * (-xy[1]) + null4[:, 2] * z + null4[:, 3]
+        e = e / np.sqrt(xy[0] ** 2 + xy[1] ** 2 + z * z + 1.0)
+        out.append(e.reshape(3, 3).T)
+    return np.stack(out) if out else np.zeros((0, 3, 3))
+
+
 # --------------------------------------------------------------------------------------- 8f rank 3: map-free aggregator
 def mapfree_correlation_aggregator(vol0, vol1):
     """mapfree_6dreg/lib/models/regression/aggregator.py:42-116 `CorrelationVolumeWarping.forward` with the shipped
