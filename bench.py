@@ -300,6 +300,7 @@ class Vit8ptB64(Workload):
         m, sd, mean, std = self._model()
         m.load_state_dict(sd)
         m = m.to(dev).eval()
+        m.force_eager = True          # the reference's plain op sequence, not the fused preprocessing / folded-BN path
         sd = {k: v.to(dev) for k, v in sd.items()}
         img, intr, lp, nc = self._inputs(pairs, 20240003)
         img, lp, nc = img.to(dev), lp.to(dev), nc.to(dev)

@@ -44,6 +44,7 @@ _SIGS = {
     "far_upsample2x_add_nhwc": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "far_scale_shift_act_nhwc": (c_int, [_P, _P, _P, c_longlong, c_int, c_float, _P]),
     "far_scale_shift_act_nhwc_out": (c_int, [_P, _P, _P, _P, c_longlong, c_int, c_float, _P]),
+    "far_vit_preprocess": (c_int, [_P, _P, c_longlong, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), _P]),
     "far_stem_conv_workspace_bytes": (c_size_t, [c_int]),
     "far_stem_conv7x7s2_relu_nhwc": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "far_pos_encode_flatten": (c_int, [_P, c_longlong, c_longlong, c_longlong, c_longlong, _P, _P, c_int, c_int, c_int,

@@ -149,9 +149,49 @@ __global__ void stem_weight_transpose_kernel(const float* __restrict__ w, float*
   if (idx < Cout * 49) wt[(idx % 49) * Cout + idx / 49] = w[idx];
 }
 
+// 8pt-ViT input preprocessing (interiornetStreetlearn_8ptVit/src/model.py:131-141): BGR -> RGB, / 255, ImageNet
+// mean / std, F.interpolate(size = out, mode = 'nearest').  Nearest-neighbour resampling commutes with per-pixel
+// arithmetic, so only the out x out sampled pixels are read (224^2 of 480 x 640: 6x fewer bytes than normalising the full
+// image first) and the arithmetic on them is the reference's, in its order: ((x / 255) - mean) / std with IEEE
+// divisions -> bit-identical to the eager sequence.  in [n, 3, H, W] (BGR, 0..255), out [n, 3, OH, OW] (RGB) NCHW.
+__global__ void __launch_bounds__(256) vit_preprocess_kernel(const float* __restrict__ img, float* __restrict__ out,
+                                                             long long total, int H, int W, int OH, int OW,
+                                                             float sy, float sx, float m0, float m1, float m2,
+                                                             float s0, float s1, float s2) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % OW);
+    const int oy = (int)((idx / OW) % OH);
+    const int c = (int)((idx / ((long long)OW * OH)) % 3);
+    const long long n = idx / ((long long)OW * OH * 3);
+    // ATen upsample_nearest: src = min(floor(dst * scale), in - 1), scale = (float)in / out
+    const int iy = min((int)floorf((float)oy * sy), H - 1), ix = min((int)floorf((float)ox * sx), W - 1);
+    const float x = img[((n * 3 + (2 - c)) * H + iy) * (long long)W + ix];
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    out[idx] = __fdiv_rn(__fsub_rn(__fdiv_rn(x, 255.0f), mean), sd);
+  }
+}
+
 }  // namespace far
 
 using namespace far;
+
+extern "C" int far_vit_preprocess(const float* images, float* out, long long n, int H, int W, int OH, int OW,
+                                  const float* mean3, const float* std3, void* stream) {
+  if (n <= 0) return FAR_OK;
+  if (images == nullptr || out == nullptr || mean3 == nullptr || std3 == nullptr || H < 1 || W < 1 || OH < 1 || OW < 1)
+    return FAR_ERR_ARG;
+  const long long total = n * 3 * OH * OW;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  vit_preprocess_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      images, out, total, H, W, OH, OW, (float)H / (float)OH, (float)W / (float)OW, mean3[0], mean3[1], mean3[2],
+      std3[0], std3[1], std3[2]);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
 
 extern "C" int far_upsample2x_add_nhwc(const float* low, const float* skip, float* out, int N, int Hin, int Win, int C,
                                        void* stream) {

@@ -95,7 +95,7 @@ int score_lse(const ScoreArgs& a, float* row_lse, float* col_lse, float* scratch
   const bool use_tc = tcws != nullptr && tcws_bytes >= tc_score_workspace_bytes(a.G, a.L, a.S, a.K) && tc_score_supported(a);
   if (used_tc) *used_tc = use_tc ? 1 : 0;
   const bool lse64 = use_tc && tc_lse64_supported(a);   // K = 64: query-tile-resident streaming kernel
-  const int pj = lse64 ? 2 : (use_tc ? 2 * JT : JT), pi = lse64 ? 4 * IT : (use_tc ? 2 * IT : IT);  // partials per row / column
+  const int pj = lse64 ? 4 : (use_tc ? 2 * JT : JT), pi = lse64 ? 4 * IT : (use_tc ? 2 * IT : IT);  // partials per row / column
   float2* colpart = rowpart + (size_t)a.G * pj * a.L;
   if (lse64) {
     int rc = tc_lse64_partials(a, rowpart, colpart, tcws, tcws_bytes, 0, st);

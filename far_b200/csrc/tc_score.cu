@@ -274,16 +274,34 @@ tc_score_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
 // (max, sum) is carried online in registers across all key tiles (one pair per row and 64-column half at the end);
 // column statistics are taken per warp (32 rows) through a warp-private 32x33 transpose -- no block-level barrier
 // anywhere in the epilogue -- and written as 4 partials per query tile.
-constexpr int L_THREADS = 64 + 256;
+constexpr int L_EPI_WARPS = 16;             // 4 per TMEM lane quarter, one 32-column chunk of the key tile each
+constexpr int L_THREADS = 64 + 32 * L_EPI_WARPS;
 constexpr int L_Q_BYTES = 4 * TILE_BYTES;
 constexpr int L_K_STAGE = 4 * TILE_BYTES;
-constexpr int L_SCR_BYTES = 8 * 32 * 33 * 4;
-constexpr size_t LSE64_SMEM = 1024 + L_Q_BYTES + 2 * L_K_STAGE + L_SCR_BYTES + 256;
+constexpr size_t LSE64_SMEM = 1024 + L_Q_BYTES + 2 * L_K_STAGE + 256;
+
+// Column sums over the 32 rows a warp owns, without shared memory: lane l holds row l's 32 column values v[0..31];
+// five exchange-and-halve steps (16 + 8 + 4 + 2 + 1 shuffles) leave the sum (or max) of column l in lane l's v[0].
+template <bool kMax>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      const float got = __shfl_xor_sync(0xffffffffu, send, off);
+      v[i] = kMax ? fmaxf(keep, got) : keep + got;
+    }
+  }
+  return v[0];
+}
 
 struct Lse64Args {
   int G, H, N, S;        // groups, heads per batch, query rows, key rows
   float scale2;
-  float2* rowpart;       // [(g*2 + half)*N + i]
+  float2* rowpart;       // [(g*4 + column chunk)*N + i]
   float2* colpart;       // [(g*4*IT + 4*it + quarter)*S + j]
 };
 
@@ -294,8 +312,7 @@ tc_lse64_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constan
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t q_base = base, k_base = base + L_Q_BYTES;
-  const uint32_t scr_base = k_base + 2 * L_K_STAGE;
-  const uint32_t bar_base = scr_base + L_SCR_BYTES;
+  const uint32_t bar_base = k_base + 2 * L_K_STAGE;
   const uint32_t q_full = bar_base;
   auto k_full = [&](int s) { return bar_base + 8u + 8u * s; };
   auto k_empty = [&](int s) { return bar_base + 24u + 8u * s; };
@@ -313,7 +330,7 @@ tc_lse64_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constan
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8);
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), L_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -381,117 +398,90 @@ tc_lse64_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constan
       __syncwarp();
     }
   } else {
-    // ===================== epilogue: 8 warps; thread = (query row, 64-key half) =====================
+    // ===================== epilogue: 16 warps; thread = (query row, 32-key chunk of the key tile) =====================
     const int ew = warp - 2;
-    const int quarter = warp & 3, half = ew >> 2;
+    const int quarter = warp & 3, c = ew >> 2;      // TMEM lane quarter of this warp; its 32-column chunk
     const int row = quarter * 32 + lane, grow = i0 + row;
     const bool rvalid = grow < p.N;
-    float(*scr)[33] = reinterpret_cast<float(*)[33]>(smem_dyn + (scr_base - raw) + (size_t)ew * 32 * 33 * 4);
     float m_run = -INFINITY, s_run = 0.f;
     for (int jt = 0; jt < JT; ++jt) {
       const int st = jt & 1;
-      const int j0 = jt * BN;
+      const int col0 = jt * BN + c * 32;
       mbar_wait(tfull_bar(st), (uint32_t)((jt >> 1) & 1));
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
-        const int col0 = j0 + c * 32;
-        uint32_t a[32], b[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(st * 2 * BN + c * 32);
-        tmem_ld32_nowait2(taddr, a);
-        tmem_ld32_nowait2(taddr + (uint32_t)BN, b);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (cc == 1) {   // this warp's part of the accumulator is in registers: hand the buffer back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(st));
-        }
-        float x[32];
-        if (rvalid && col0 + 32 <= p.S) {
+      uint32_t a[32], b[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(st * 2 * BN + c * 32);
+      tmem_ld32_nowait2(taddr, a);
+      tmem_ld32_nowait2(taddr + (uint32_t)BN, b);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();           // this warp's part of the accumulator is in registers: hand the buffer back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(st));
+      float x[32];
+      if (rvalid && col0 + 32 <= p.S) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) x[e] = (__uint_as_float(a[e]) + __uint_as_float(b[e])) * p.scale2;
-        } else {
+        for (int e = 0; e < 32; ++e) x[e] = (__uint_as_float(a[e]) + __uint_as_float(b[e])) * p.scale2;
+      } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            x[e] = (rvalid && col0 + e < p.S) ? (__uint_as_float(a[e]) + __uint_as_float(b[e])) * p.scale2 : -INFINITY;
-        }
-        // ---- ONE exponential per score serves the row and the column statistics: E = 2^(x - R) with R the maximum of
-        // this warp's 32 x 32 chunk (warp shuffle reduce, no block barrier).  Any reference >= the data is a valid
-        // log-sum-exp shift; what a shared reference can lose is a term that underflows (ex2.approx.ftz flushes below
-        // 2^-126), so the shared path is taken only when the whole chunk lies within 100 binades of R (warp-uniform test;
-        // otherwise, and for ragged edge chunks with -inf padding, the exact per-row / per-column maxima below).
-        float c0 = fmaxf(x[0], x[4]), c1 = fmaxf(x[1], x[5]), c2 = fmaxf(x[2], x[6]), c3 = fmaxf(x[3], x[7]);
-        float d0 = fminf(x[0], x[4]), d1 = fminf(x[1], x[5]), d2 = fminf(x[2], x[6]), d3 = fminf(x[3], x[7]);
-#pragma unroll
-        for (int e = 8; e < 32; e += 4) {
-          c0 = fmaxf(c0, x[e]); c1 = fmaxf(c1, x[e + 1]); c2 = fmaxf(c2, x[e + 2]); c3 = fmaxf(c3, x[e + 3]);
-          d0 = fminf(d0, x[e]); d1 = fminf(d1, x[e + 1]); d2 = fminf(d2, x[e + 2]); d3 = fminf(d3, x[e + 3]);
-        }
-        const float tmx = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
-        const float R = warp_max(tmx);
-        const float mn = -warp_max(-fminf(fminf(d0, d1), fminf(d2, d3)));
-        const int col = col0 + lane;
-        if (R - mn <= 100.f) {   // (false for NaN / -inf padding)
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            x[e] = ex2(x[e] - R); x[e + 1] = ex2(x[e + 1] - R); x[e + 2] = ex2(x[e + 2] - R); x[e + 3] = ex2(x[e + 3] - R);
-            a0 += x[e]; a1 += x[e + 1]; a2 += x[e + 2]; a3 += x[e + 3];
-          }
-          const float m_new = fmaxf(m_run, R);
-          s_run = s_run * ex2(m_run - m_new) + ((a0 + a1) + (a2 + a3)) * ex2(R - m_new);
-          m_run = m_new;
-          // column sums of this warp's 32 rows: warp-private transpose of the exponentials
-#pragma unroll
-          for (int e = 0; e < 32; ++e) scr[lane][e] = x[e];
-          __syncwarp();
-          a0 = a1 = a2 = a3 = 0.f;
-#pragma unroll
-          for (int r = 0; r < 32; r += 4) {
-            a0 += scr[r][lane]; a1 += scr[r + 1][lane]; a2 += scr[r + 2][lane]; a3 += scr[r + 3][lane];
-          }
-          if (col < p.S) p.colpart[((size_t)g * 4 * IT + 4 * it + quarter) * p.S + col] = make_float2(R, (a0 + a1) + (a2 + a3));
-          __syncwarp();   // the next chunk overwrites scr
-          continue;
-        }
-        // ---- exact path: row statistics, online across key tiles (4 independent chains)
-        const float m_new = fmaxf(m_run, tmx);
-        if (m_new > -INFINITY) {
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            a0 += ex2(x[e] - m_new); a1 += ex2(x[e + 1] - m_new); a2 += ex2(x[e + 2] - m_new); a3 += ex2(x[e + 3] - m_new);
-          }
-          s_run = s_run * ex2(m_run - m_new) + ((a0 + a1) + (a2 + a3));
-          m_run = m_new;
-        }
-        // ---- column statistics of this warp's 32 rows: warp-private transpose
-#pragma unroll
-        for (int e = 0; e < 32; ++e) scr[lane][e] = x[e];
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < 32; ++r) x[r] = scr[r][lane];
-        c0 = fmaxf(x[0], x[4]); c1 = fmaxf(x[1], x[5]); c2 = fmaxf(x[2], x[6]); c3 = fmaxf(x[3], x[7]);
-#pragma unroll
-        for (int r = 8; r < 32; r += 4) {
-          c0 = fmaxf(c0, x[r]); c1 = fmaxf(c1, x[r + 1]); c2 = fmaxf(c2, x[r + 2]); c3 = fmaxf(c3, x[r + 3]);
-        }
-        const float cmx = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
-        float cs = 0.f;
-        if (cmx > -INFINITY) {
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-          for (int r = 0; r < 32; r += 4) {
-            a0 += ex2(x[r] - cmx); a1 += ex2(x[r + 1] - cmx); a2 += ex2(x[r + 2] - cmx); a3 += ex2(x[r + 3] - cmx);
-          }
-          cs = (a0 + a1) + (a2 + a3);
-        }
-        if (col < p.S) p.colpart[((size_t)g * 4 * IT + 4 * it + quarter) * p.S + col] = make_float2(cmx, cs);
-        __syncwarp();   // the next chunk overwrites scr
+        for (int e = 0; e < 32; ++e)
+          x[e] = (rvalid && col0 + e < p.S) ? (__uint_as_float(a[e]) + __uint_as_float(b[e])) * p.scale2 : -INFINITY;
       }
+      // ---- ONE exponential per score serves the row and the column statistics: E = 2^(x - R) with R the maximum of
+      // this warp's 32 x 32 chunk (warp shuffle reduce, no block barrier).  Any reference >= the data is a valid
+      // log-sum-exp shift; what a shared reference can lose is a term that underflows (ex2.approx.ftz flushes below
+      // 2^-126), so the shared path is taken only when the whole chunk lies within 100 binades of R (warp-uniform test;
+      // otherwise, and for ragged edge chunks with -inf padding, the exact per-row / per-column maxima below).
+      float c0 = fmaxf(x[0], x[4]), c1 = fmaxf(x[1], x[5]), c2 = fmaxf(x[2], x[6]), c3 = fmaxf(x[3], x[7]);
+      float d0 = fminf(x[0], x[4]), d1 = fminf(x[1], x[5]), d2 = fminf(x[2], x[6]), d3 = fminf(x[3], x[7]);
+#pragma unroll
+      for (int e = 8; e < 32; e += 4) {
+        c0 = fmaxf(c0, x[e]); c1 = fmaxf(c1, x[e + 1]); c2 = fmaxf(c2, x[e + 2]); c3 = fmaxf(c3, x[e + 3]);
+        d0 = fminf(d0, x[e]); d1 = fminf(d1, x[e + 1]); d2 = fminf(d2, x[e + 2]); d3 = fminf(d3, x[e + 3]);
+      }
+      const float tmx = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
+      const float R = warp_max(tmx);
+      const float mn = -warp_max(-fminf(fminf(d0, d1), fminf(d2, d3)));
+      const int col = col0 + lane;
+      float2* cp = p.colpart + ((size_t)g * 4 * IT + 4 * it + quarter) * p.S;
+      if (R - mn <= 100.f) {   // (false for NaN / -inf padding)
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          x[e] = ex2(x[e] - R); x[e + 1] = ex2(x[e + 1] - R); x[e + 2] = ex2(x[e + 2] - R); x[e + 3] = ex2(x[e + 3] - R);
+          a0 += x[e]; a1 += x[e + 1]; a2 += x[e + 2]; a3 += x[e + 3];
+        }
+        const float m_new = fmaxf(m_run, R);
+        s_run = s_run * ex2(m_run - m_new) + ((a0 + a1) + (a2 + a3)) * ex2(R - m_new);
+        m_run = m_new;
+        const float cs = warp_transpose_reduce<false>(x, lane);   // column sums of the exponentials over the 32 rows
+        if (col < p.S) cp[col] = make_float2(R, cs);
+        continue;
+      }
+      // ---- exact path: row statistics, online across key tiles
+      const float m_new = fmaxf(m_run, tmx);
+      if (m_new > -INFINITY) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          a0 += ex2(x[e] - m_new); a1 += ex2(x[e + 1] - m_new); a2 += ex2(x[e + 2] - m_new); a3 += ex2(x[e + 3] - m_new);
+        }
+        s_run = s_run * ex2(m_run - m_new) + ((a0 + a1) + (a2 + a3));
+        m_run = m_new;
+      }
+      // ---- column statistics of this warp's 32 rows: per-column maximum, then exponentials relative to it
+      float y[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) y[e] = x[e];
+      const float cmx = warp_transpose_reduce<true>(y, lane);      // lane l: max of column l over the 32 rows
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float cm = __shfl_sync(0xffffffffu, cmx, e);
+        x[e] = cm > -INFINITY ? ex2(x[e] - cm) : 0.f;
+      }
+      const float cs = warp_transpose_reduce<false>(x, lane);
+      if (col < p.S) cp[col] = make_float2(cmx, cs);
     }
-    if (rvalid) p.rowpart[((size_t)g * 2 + half) * p.N + grow] = make_float2(m_run, s_run);
+    if (rvalid) p.rowpart[((size_t)g * 4 + c) * p.N + grow] = make_float2(m_run, s_run);
   }
 
   tc_fence_before();

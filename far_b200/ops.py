@@ -174,6 +174,23 @@ def scale_shift_act_(x, scale, shift, negative_slope):
     return x
 
 
+def vit_preprocess(images, out_size=224, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """ViTEss.extract_features input preprocessing (interiornetStreetlearn_8ptVit/src/model.py:131-141) in one kernel:
+    images [n,3,H,W] fp32 BGR 0..255 (contiguous) -> [n,3,out,out] normalised RGB, nearest resize; bit-identical to
+    `F.interpolate((images[:, [2,1,0]] / 255 - mean) / std, size=out)`."""
+    import ctypes
+    lib = L.load()
+    if not (images.is_cuda and images.dtype == torch.float32 and images.is_contiguous() and images.dim() == 4
+            and images.shape[1] == 3):
+        raise L.FarError("vit_preprocess needs a contiguous fp32 CUDA [n,3,H,W] tensor")
+    n, _, H, W = images.shape
+    out = torch.empty((n, 3, out_size, out_size), dtype=torch.float32, device=images.device)
+    m3, s3 = (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std)
+    check(lib.far_vit_preprocess(ptr(images), ptr(out), n, H, W, out_size, out_size, m3, s3, stream()),
+          "far_vit_preprocess")
+    return out
+
+
 def scale_shift_act(x, scale, shift, negative_slope):
     """Out-of-place leaky_relu(x*scale[c] + shift[c]) on a channels_last [N,C,H,W] map: the pre-activation
     relu(bn(x)) of the map-free PreAct blocks (encoder/preact.py:35,68), x stays alive as the identity shortcut."""

@@ -248,6 +248,9 @@ class ViTEss(nn.Module):
         return intrinsics
 
     def extract_features(self, images, intrinsics=None):
+        if images.is_cuda and not self.training and not torch.is_grad_enabled() and images.dtype == torch.float32 \
+                and not getattr(self, 'force_eager', False):
+            return self._extract_features_fused(images, intrinsics)
         images = images[:, :, [2, 1, 0]] / 255.0
         mean = torch.as_tensor([0.485, 0.456, 0.406], device=images.device)
         std = torch.as_tensor([0.229, 0.224, 0.225], device=images.device)
@@ -260,6 +263,69 @@ class ViTEss(nn.Module):
         x = self.extractor_final_conv(x)
         n = x.shape[0]
         feats = x.reshape(n, -1, self.num_patches)[:, :self.total_num_features].permute(0, 2, 1)
+        return feats, intrinsics
+
+    # ---- eval-time fused path (same arithmetic): one preprocessing kernel, eval BatchNorm folded into the convolutions,
+    # cuDNN conv+bias(+residual)+ReLU fused calls (channels_last) -- removes ~45 elementwise / BN launches per batch
+    def _folded(self):
+        mods = [self.resnet.conv1, self.resnet.bn1, self.resnet.layer1, self.resnet.layer2, self.extractor_final_conv]
+        ts = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
+        key = tuple(int(t._version) for t in ts) + (self.resnet.conv1.weight.data_ptr(),)
+        c = getattr(self, "_fold_cache", None)
+        if c is not None and c[0] == key:
+            return c[1]
+
+        def fold(conv, bn):
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            w = (conv.weight * scale[:, None, None, None]).contiguous(memory_format=torch.channels_last)
+            b0 = conv.bias if conv.bias is not None else torch.zeros_like(bn.running_mean)
+            return w, ((b0 - bn.running_mean) * scale + bn.bias).contiguous()
+
+        with torch.no_grad():
+            f = {"stem": fold(self.resnet.conv1, self.resnet.bn1)}
+            for li, layer in enumerate((self.resnet.layer1, self.resnet.layer2)):
+                for bi, blk in enumerate(layer):
+                    f[(li, bi, 1)] = fold(blk.conv1, blk.bn1)
+                    f[(li, bi, 2)] = fold(blk.conv2, blk.bn2)
+                    if blk.downsample is not None:
+                        wd, bd = fold(blk.downsample[0], blk.downsample[1])
+                        f[(li, bi, "d")] = wd
+                        f[(li, bi, 2)] = (f[(li, bi, 2)][0], (f[(li, bi, 2)][1] + bd).contiguous())
+            e = self.extractor_final_conv
+            f["e1"], f["e2"] = fold(e.conv1, e.norm1), fold(e.conv2, e.norm2)
+            if e.downsample is not None:
+                f["ed"] = fold(e.downsample[0], e.downsample[1])
+        self._fold_cache = (key, f)
+        return f
+
+    def _extract_features_fused(self, images, intrinsics):
+        B = images.shape[0]
+        shape = images.shape
+        x = ops.vit_preprocess(images.reshape(B * 2, 3, shape[-2], shape[-1]).contiguous(), 224)
+        if intrinsics is not None:
+            intrinsics = self.update_intrinsics(shape, intrinsics)
+        f = self._folded()
+        one, pad1 = (1, 1), (1, 1)
+        r = self.resnet
+        w, b = f["stem"]
+        x = torch.relu_(F.conv2d(x.contiguous(memory_format=torch.channels_last), w, b, stride=2, padding=3))
+        x = r.maxpool(x)
+        for li, layer in enumerate((r.layer1, r.layer2)):
+            for bi, blk in enumerate(layer):
+                w1, b1 = f[(li, bi, 1)]
+                w2, b2 = f[(li, bi, 2)]
+                y = torch.cudnn_convolution_relu(x, w1, b1, blk.conv1.stride, pad1, one, 1)
+                if blk.downsample is not None:   # relu(conv2(y) + b2 + conv_d(x) + b_d): the bias rides on conv2's
+                    x = F.conv2d(x, f[(li, bi, "d")], None, stride=blk.downsample[0].stride)
+                x = torch.cudnn_convolution_add_relu(y, w2, x, 1.0, b2, one, pad1, one, 1)
+        e = self.extractor_final_conv
+        y = torch.cudnn_convolution_relu(x, f["e1"][0], f["e1"][1], e.conv1.stride, e.conv1.padding, one, 1)
+        y = torch.relu_(F.conv2d(y, f["e2"][0], f["e2"][1], e.conv2.stride, e.conv2.padding))
+        if e.downsample is not None:
+            x = F.conv2d(x, f["ed"][0], f["ed"][1], e.downsample[0].stride, e.downsample[0].padding)
+        x = torch.relu_(x + y)
+        n = x.shape[0]
+        feats = x.contiguous().reshape(n, -1, self.num_patches)[:, :self.total_num_features].permute(0, 2, 1)
         return feats, intrinsics
 
     def fusion_head(self, features, intrinsics, loftr_num_corr, loftr_preds):

@@ -103,6 +103,12 @@ int far_scale_shift_act_nhwc(float* x, const float* scale, const float* shift, l
  * alive as the identity shortcut (mapfree_6dreg/lib/models/regression/encoder/preact.py:35-41, 68-74). */
 int far_scale_shift_act_nhwc_out(const float* x, float* y, const float* scale, const float* shift, long long pixels,
                                  int C, float negative_slope, void* stream);
+/* 8pt-ViT input preprocessing (interiornetStreetlearn_8ptVit/src/model.py:131-141): images [n,3,H,W] fp32 BGR 0..255 ->
+ * out [n,3,OH,OW] RGB = nearest-resize(((x / 255) - mean) / std), the reference's arithmetic on exactly the pixels
+ * F.interpolate(mode='nearest') samples (resize and per-pixel arithmetic commute: bit-identical, 6x fewer bytes read).
+ * mean3 / std3: HOST pointers to the 3 RGB constants. */
+int far_vit_preprocess(const float* images, float* out, long long n, int H, int W, int OH, int OW, const float* mean3,
+                       const float* std3, void* stream);
 /* Backbone stem: y = relu(conv2d(x, w, stride 2, padding 3) + bias) for a ONE-channel input and a 7x7 kernel,
  * x:[N,1,H,W] fp32, w:[Cout,1,7,7] (eval BatchNorm folded in), y:[N,OH,OW,Cout] NHWC, Cout == 128.
  * Replaces `self.relu(self.bn1(self.conv1(x)))` (mp3d_loftr/src/loftr/backbone/resnet_fpn.py:52-54,80); cuDNN has no

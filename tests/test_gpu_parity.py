@@ -638,3 +638,32 @@ def test_pl_loftr_test_step_flow(tmp_path):
     assert torch.allclose(saved[:, :3], m["pred_R"][0].double(), atol=1e-12)
     lp, nc = pred_cache.load_prediction(str(tmp_path), "test", "17")
     assert tuple(lp.shape) == (1, 3, 4) and int(nc[0]) == 0
+
+
+def test_vit_preprocess_and_fused_extractor():
+    """far_vit_preprocess is BIT-identical to the reference's eager preprocessing (model.py:131-141: BGR->RGB, /255,
+    ImageNet mean / std, nearest resize to 224) at 480x640 and at a non-integer ratio; the folded-BN / fused-cuDNN
+    extractor equals the plain module graph to conv rounding."""
+    from far_b200.vit8pt import ViTEss
+    g = np.random.default_rng(3)
+    for (H, W) in ((480, 640), (301, 517)):
+        img = torch.from_numpy(g.integers(0, 256, size=(4, 3, H, W), dtype=np.uint8)).float()
+        got = ops.vit_preprocess(cu(img), 224).cpu()
+        x = img[:, [2, 1, 0]] / 255.0
+        mean, std = torch.tensor([0.485, 0.456, 0.406]), torch.tensor([0.229, 0.224, 0.225])
+        ref = torch.nn.functional.interpolate(cu(x.sub_(mean[:, None, None]).div_(std[:, None, None])), size=224).cpu()
+        assert torch.equal(got, ref), (H, W, (got - ref).abs().max())
+    mean9 = torch.tensor([0.0, 0.0, 0.5, 0.9, 0.0, 0.0, 0.0, 0.9, 0.0])
+    std9 = torch.tensor([0.3, 0.2, 0.4, 0.1, 0.1, 0.2, 0.1, 0.1, 0.2])
+    model = ViTEss(_vit_args(), mean9, std9)
+    _load(model, synth.synth_state_dict(model.state_dict(), 5))
+    imgs = torch.from_numpy(g.integers(0, 256, size=(3, 2, 3, 480, 640), dtype=np.uint8)).float()
+    intr = torch.tensor([[[128.0, 128.0, 128.0, 128.0]] * 2] * 3)
+    with torch.no_grad():
+        f_fused, i_fused = model.extract_features(cu(imgs), intr.clone())
+        model.force_eager = True
+        f_eager, i_eager = model.extract_features(cu(imgs), intr.clone())
+        model.force_eager = False
+    assert torch.equal(i_fused, i_eager) and f_fused.shape == f_eager.shape == (6, 576, 192)
+    scale = f_eager.abs().max().item()
+    assert (f_fused - f_eager).abs().max().item() < 2e-5 * max(scale, 1.0), ((f_fused - f_eager).abs().max(), scale)
