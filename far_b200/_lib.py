@@ -34,6 +34,7 @@ _SIGS = {
     "far_abi_version": (c_int, []),
     "far_launch_count": (ctypes.c_ulonglong, []),
     "far_tc_set_cross16": (c_int, [c_int]),
+    "far_tc_debug_counters": (c_int, [c_int, _P]),
     "far_tc_weight_split_bytes": (c_size_t, [c_int, c_int]),
     "far_tc_weight_split": (c_int, [_P, c_int, c_int, c_int, _P, c_size_t, _P]),
     "far_linear_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

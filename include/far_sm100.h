@@ -56,6 +56,14 @@ int far_profile_read(int id, double* total_ms, unsigned long long* launches, dou
  * (tests/test_gpu_tcgen05.py); the score / EMM kernels always use tf32 cross terms. */
 int far_tc_set_cross16(int on);
 
+/* Diagnostics of the TMEM-operand GEMM kernels (kernel = 0: csrc/tc_gemm_ts.cu, 1: the CTA-pair kernel
+ * csrc/tc_gemm_pair.cu): with env FAR_TC_DBG bit 256 set, CTA 0 of every launch accounts, per warp role, the cycles spent
+ * waiting on each pipeline barrier; this reads the 16 counters of the last launch (layout documented at g_ts_prof).
+ * kernel = 2: `out16` must hold 256 entries and receives the clock64 timeline of one tile of the pair kernel (g_tp_trace).
+ * kernel = 3 (FAR_TC_DBG bit 1024): 320 entries, (total cycles, tiles) of every CTA of the last pair-kernel launch.
+ * Returns 0, or -1 on a CUDA error. */
+int far_tc_debug_counters(int kernel, unsigned long long* out16);
+
 /* ---- nn.Linear family --------------------------------------------------------------------------------
  * y[M,N] = act( [x1 | x2] * W^T + bias ),  x1:[M,K1] (ld ldx1), x2:[M,K2] (ld ldx2, may be NULL with K2=0),
  * W:[N,K1+K2] (ld ldw), bias:[N] or NULL, act applied to columns < act_cols only (act_cols<0: all).
