@@ -17,14 +17,17 @@ lib = _lib.load()
 M = int(os.environ.get("M", 153600))
 shapes = {"256x256": (256, 256, ACT_NONE, False), "256x256_elu": (256, 256, ACT_ELU1, False), "512x256": (512, 256, ACT_NONE, False),
           "512x512_2seg_relu": (512, 512, ACT_RELU, True), "256x512": (256, 512, ACT_NONE, False)}
+ONLY = os.environ.get("ONLY")
 for name, (N, K, act, two) in shapes.items():
+    if ONLY and name != ONLY:
+        continue
     if two:
         x = torch.randn(M, K // 2, device="cuda"); x2 = torch.randn(M, K // 2, device="cuda")
     else:
         x = torch.randn(M, K, device="cuda"); x2 = None
     w = torch.randn(N, K, device="cuda") * 0.05
     y = torch.empty(M, N, device="cuda")
-    for _ in range(10):
+    for _ in range(int(os.environ.get("WARM", 10))):
         ops.linear(x, w, None, act, x2=x2, engine=ENGINE_TCGEN05, out=y)
     torch.cuda.synchronize()
     ts = []

@@ -14,7 +14,8 @@ from far_b200._lib import ENGINE_TCGEN05, ACT_NONE, ACT_ELU1, ACT_RELU
 
 lib = _lib.load()
 KERNEL = 1 if os.environ.get("FAR_TC_TS", "2") == "2" else 0   # which kernel's counters: 1 = CTA-pair, 0 = one-CTA TS
-M = 153600
+M = int(os.environ.get("M", 153600))
+WARM = int(os.environ.get("WARM", 10))
 names = ["prod wait_empty", "prod total", "mma wait_main", "mma wait_cross", "mma wait_conv", "mma total",
          "conv wait_full", "conv wait_afree", "conv total", "epi wait_tfull", "epi total", "epi tfull->cross", "(tiles)", "(k-blocks)", "prod prefetch", "prod tma issue"]
 for name, (N, K, act, two) in {"256x256": (256, 256, ACT_NONE, False), "256x256_elu": (256, 256, ACT_ELU1, False),
@@ -25,7 +26,7 @@ for name, (N, K, act, two) in {"256x256": (256, 256, ACT_NONE, False), "256x256_
         x = torch.randn(M, K, device="cuda"); x2 = None
     w = torch.randn(N, K, device="cuda") * 0.05
     y = torch.empty(M, N, device="cuda")
-    for _ in range(10):
+    for _ in range(WARM):
         ops.linear(x, w, None, act, x2=x2, engine=ENGINE_TCGEN05, out=y)
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

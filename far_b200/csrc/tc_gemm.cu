@@ -498,9 +498,10 @@ int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
   const int tiles = G * ceil_div(L, BM) * ceil_div(N, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   ProfScope prof(PROF_TC_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)Gb * N * K + (double)M * N), st);
-  // raw fp32 activations: the A operand goes through TMEM; FAR_TC_TS = 2 (default) CTA pairs sharing B (tc_gemm_pair.cu),
-  // 1 one CTA per tile (tc_gemm_ts.cu), 0 the all-shared-memory kernel below
-  static const int ts_mode = getenv("FAR_TC_TS") ? atoi(getenv("FAR_TC_TS")) : 2;
+  // raw fp32 activations: the A operand goes through TMEM.  FAR_TC_TS = 1 (default): one CTA per 128 x 128 tile
+  // (tc_gemm_ts.cu); 2: CTA pairs sharing B (tc_gemm_pair.cu: 13 % faster than mode 1 on an idle GPU, 15-20 % slower inside
+  // the power-capped step); 0: the all-shared-memory kernel below
+  static const int ts_mode = getenv("FAR_TC_TS") ? atoi(getenv("FAR_TC_TS")) : 1;
   const int pair_clusters = (rawA && !cross16 && ts_mode >= 2) ? gemm_pair_max_clusters() : 0;
   if (pair_clusters > 0) {
     CUtensorMap mBhi2, mBlo2;   // 64-row boxes: each CTA of a pair loads its half of the 128 B rows

@@ -162,13 +162,29 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_cons
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
-    // (no L2 prefetch of A here: cp.async.bulk.prefetch.tensor blocks the issuing thread ~650 cycles per tile when the
-    // TMA queue is busy -- measured as 60 % of the producer's time -- and with 6 x 32 KB stages in flight it buys nothing)
+    // L2 prefetch of the raw A tiles PF k-blocks ahead (diagnostics bit 8192 enables it; off by default:
+    // cp.async.bulk.prefetch.tensor blocks the issuing thread ~650 cycles per k-block when the TMA queue is busy)
+    constexpr int PF = 8;
+    auto prefetch_a = [&](int tile_p, int kb_p) {
+      if (tile_p >= num_tiles) return;
+      const int tm_p = tile_p / tiles_n;
+      const int g_p = tm_p / tiles_pg, r0_p = (tm_p % tiles_pg) * 2 * BM + (int)rank * BM;
+      if (r0_p >= p.L) return;
+      if (kb_p < p.kb1) tma_prefetch_4d(&mapA1, kb_p * BK, r0_p, g_p, 0);
+      else tma_prefetch_4d(&mapA2, (kb_p - p.kb1) * BK, r0_p, g_p, 0);
+    };
     long long w_empty = 0, w_pref = 0, w_issue = 0, t_begin = TP_CLKH();
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int tm = tile / tiles_n, n0 = (tile % tiles_n) * BN;
       const int g = tm / tiles_pg, r0 = (tm % tiles_pg) * 2 * BM + (int)rank * BM, gb = p.b_grouped ? g : 0;
       for (int kb = 0; kb < kblocks; ++kb) {
+        if (p.dbg & 8192) {
+          if (elect_one()) {
+            const int ahead = kb + PF;
+            prefetch_a(tile + (ahead / kblocks) * num_pairs, ahead % kblocks);
+          }
+          __syncwarp();
+        }
         const long long c0 = TP_CLKH();
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const long long ci = TP_CLKH();
