@@ -576,7 +576,8 @@ def run_reference(args, rank, world):
 
 # ======================================================================================================= our arm
 ALGO_NOTE = {
-    "tc_gemm_kernel": "3xTF32 error-compensated fp32 GEMM: 3 tensor-core MMAs per algorithmic FMA, so frac <= 1/3 of the "
+    "tc_gemm_kernel": "all launches of the 3xTF32 GEMM engine (tc_gemm_ts_kernel: A operand through TMEM, raw fp32 activations; "
+                      "tc_gemm_kernel for pre-split A).  3 tensor-core MMAs per algorithmic FMA, so frac <= 1/3 of the "
                       "tf32 pipe (= 1/6 of the bf16 peak used as denominator)",
     "tc_emm_pv_kernel": "3xTF32 S = QK^T and P V' (A operand from TMEM): same 1/6 ceiling; algorithmic FLOPs of SURVEY 8d",
     "tc_score_kernel": "3xTF32 score tiles + one MUFU.EX2 per exponential (MUFU co-bound); includes tc_lse64",

@@ -230,6 +230,11 @@ def test_eight_point_properties_large():
     Et = tx @ Rg.double()
     d = f_distance(F, Et)
     assert d.median() < 5e-3 and d.max() < 0.1, (d.median(), d.max())
+    # and against the fp64 oracle at the full N = 2048 (a slice of the pairs: the oracle builds N x N weight matrices)
+    sl = slice(0, P, 32)
+    Fo = O.run_8point(p1[sl].double(), p2[sl].double(), w[sl].double())
+    do = f_distance(F[sl], Fo)
+    assert do.max() < 1e-4, f"N = 2048: Frobenius distance to the fp64 oracle {do.max():.3e}"
 
 
 def test_essential_decompose(golden_dir):
@@ -421,15 +426,17 @@ def test_pair_batch_equals_independent_b1_evaluations():
 
 def test_dual_softmax_config5_size_properties():
     """BASELINE configs[4] shape (L = S = 2048 tokens, 32x64 grid, border 0, thr 0) on 6 pairs: bit-exact indices
-    against the oracle for one pair, and size-independent properties for all: mutual-nearest-neighbour (no i or j
+    against the oracle for every pair, and size-independent properties: mutual-nearest-neighbour (no i or j
     repeats), ascending (b,i) order, 0 < conf <= 1."""
     g = O.rng(55)
     P = 6
     c0, c1 = O.randn(g, P, 2048, 256, scale=2.5), O.randn(g, P, 2048, 256, scale=2.5)
     d = _match(c0, c1, (32, 64), (32, 64), 0.0, 0)
-    o = O.coarse_matching(c0[:1], c1[:1], (32, 64), (32, 64), 0.0, 0, 0.1, 8.0)
     b, i, j, mc = d["b_ids"].cpu(), d["i_ids"].cpu(), d["j_ids"].cpu(), d["mconf"].cpu()
-    assert torch.equal(i[b == 0], o["i_ids"]) and torch.equal(j[b == 0], o["j_ids"])
+    for q in range(P):   # every pair against the oracle (one at a time: 2048^2 fp32 matrices)
+        o = O.coarse_matching(c0[q:q + 1], c1[q:q + 1], (32, 64), (32, 64), 0.0, 0, 0.1, 8.0)
+        assert torch.equal(i[b == q], o["i_ids"]) and torch.equal(j[b == q], o["j_ids"]), f"pair {q}: match indices"
+        assert_close(mc[b == q], o["mconf"], 1e-6, 1e-4, f"pair {q}: mconf")
     key = b * 2048 + i
     assert torch.all(key[1:] > key[:-1]), "ascending (b, i), each i at most once"
     assert torch.unique(b * 2048 + j).numel() == j.numel(), "each j at most once per pair (mutual NN)"
@@ -439,7 +446,7 @@ def test_dual_softmax_config5_size_properties():
 
 def test_vitess_batch64_matches_per_sample():
     """BASELINE configs[2] (8pt-ViT + cached-correspondence solver inputs, batch 64): the batched forward equals the
-    per-sample forward (the head is properly batched in the reference, vision_transformer.py:177-283)."""
+    per-sample forward (the head is properly batched in the reference, vision_transformer.py:177-283) AND the oracle."""
     from far_b200.vit8pt import ViTEss
     mean = torch.tensor([0.0, 0.0, 0.5, 0.9, 0.0, 0.0, 0.0, 0.9, 0.0])
     std = torch.tensor([0.3, 0.2, 0.4, 0.1, 0.1, 0.2, 0.1, 0.1, 0.2])
@@ -459,6 +466,14 @@ def test_vitess_batch64_matches_per_sample():
                                         lp[b0:b0 + 1])
             assert_close(full[b0:b0 + 1], one, 2e-5, 1e-5, f"sample {b0}: pose")
             assert_close(wt[b0:b0 + 1], w1, 2e-5, 1e-5, f"sample {b0}: gate")
+        # and the batch-64 result against the oracle (vision_transformer.py restated), on a slice of the samples
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        for b0 in (0, 17, 40, 63):
+            pos = O.emm_positional_encodings_vit(intr[b0:b0 + 1])
+            to, Ro, r6o, wto = O.vit_fusion_head(sd, feats[2 * b0:2 * b0 + 2], pos, lp[b0:b0 + 1], nc[b0:b0 + 1], mean, std)
+            assert_close(full[b0:b0 + 1, 3:], r6o, 1e-4, 1e-4, f"sample {b0}: normalised 6-D rotation vs oracle")
+            assert_close(full[b0:b0 + 1, :3] * std[:3] + mean[:3], to, 1e-4, 1e-4, f"sample {b0}: translation vs oracle")
+            assert_close(wt[b0:b0 + 1], wto, 1e-4, 1e-4, f"sample {b0}: gate vs oracle")
 
 
 # ------------------------------------------------------------------------------------------- 8pt-ViT / map-free heads

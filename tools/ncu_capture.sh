@@ -9,7 +9,7 @@
 # The bench runs WITHOUT the CUDA graph (--no-graph) so every kernel is an ordinary launch for the profiler, and without
 # the baselines; numbers printed by a bench run under ncu are never bench values.
 set -x
-TAG=${1:-r2}
+TAG=${1:-r3}
 mkdir -p gpurun_out
 F="--no-cpu-baseline --no-gpu-eager-baseline --no-graph"
 B="python bench.py --steps 1 --warmup 3 $F"
@@ -31,7 +31,7 @@ if [ "$2" == "full" ]; then
     ncu -i gpurun_out/$1.ncu-rep --page source --csv --print-source sass --launch-skip $2 --launch-count 1 > gpurun_out/$1_src.csv 2>/dev/null
     rm -f gpurun_out/$1.ncu-rep
   }
-  $NCU -k regex:tc_gemm_kernel -s 60 -c 10 -f -o gpurun_out/${TAG}_tc_gemm $B1 > gpurun_out/ncu_gemm.log 2>&1
+  $NCU -k regex:'tc_gemm' -s 60 -c 10 -f -o gpurun_out/${TAG}_tc_gemm $B1 > gpurun_out/ncu_gemm.log 2>&1
   export_rep ${TAG}_tc_gemm 2
   $NCU -k regex:'tc_emm_pv_kernel|tc_lse64_kernel' -s 0 -c 2 -f -o gpurun_out/${TAG}_tc_emm $B1 > gpurun_out/ncu_emm.log 2>&1
   export_rep ${TAG}_tc_emm 0

@@ -7,7 +7,7 @@ import csv
 import json
 import sys
 
-CLASSES = {"tc_gemm_kernel": "tc_gemm_kernel", "tc_score_kernel": ("tc_score_kernel", "tc_lse64_kernel"), "tc_emm_pv_kernel": "tc_emm_pv_kernel",
+CLASSES = {"tc_gemm_kernel": ("tc_gemm_kernel", "tc_gemm_ts_kernel", "tc_gemm_pair_kernel"), "tc_score_kernel": ("tc_score_kernel", "tc_lse64_kernel"), "tc_emm_pv_kernel": "tc_emm_pv_kernel",
            "la_reduce": ("la_reduce_allheads_kernel", "la_reduce_kv_async_kernel"), "eightpt_kernels": "eightpt",
            "solver": ("ransac_", "pose_select", "essential_to_cand"), "la_apply": "la_apply_allheads_kernel", "la_small_kernel": "la_small",
            "layernorm": "layernorm", "linear_simt_kernel": "linear_simt_kernel", "fpn_fuse": "stem_conv7x7s2",
