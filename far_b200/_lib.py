@@ -73,6 +73,7 @@ _SIGS = {
     "far_prior_ransac_score": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, c_int, c_float, c_float, _P, _P, _P,
                                        _P, _P, _P]),
     "far_segment_offsets": (c_int, [_P, c_longlong, c_int, _P, _P]),
+    "far_five_point": (c_int, [_P, c_int, _P, _P, _P]),
     "far_ransac_sample_models_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int]),
     "far_ransac_sample_models": (c_int, [_P, _P, _P, c_longlong, c_int, _P, _P, _P, c_float, c_int, c_int,
                                          ctypes.c_ulonglong, _P, _P, _P, c_size_t, _P]),

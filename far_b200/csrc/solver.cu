@@ -13,6 +13,7 @@
 //   right-singular vector of F_hat (3x3 Jacobi in fp64 on F^T F):  F_hat - (F_hat v3) v3^T  ==  U diag(s1,s2,0) V^T;
 //   de-normalise  T2^T F T1 ; divide by (F22 + 1e-8) when |F22| > 1e-8.
 #include "common.cuh"
+#include "fivept.cuh"
 
 namespace far {
 
@@ -710,25 +711,12 @@ __global__ void __launch_bounds__(256) ransac_cdf_kernel(RaggedPts pts, int P, c
   }
 }
 
+// S distinct indices of a pair's n correspondences for hypothesis g: inverse-CDF draws from the counter-based stream
+// (seed; g, block), a draw that repeats an index already in the sample is redrawn (up to 4 times, next words).
 template <int S>
-__global__ void __launch_bounds__(128) ransac_sample_kernel(RaggedPts pts, int P, int H, const double* __restrict__ cdf,
-                                                            unsigned long long seed, double* __restrict__ rec,
-                                                            int* __restrict__ idx_out) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= P * H) return;
-  const int pair = g / H;
-  const int n = pts.count(pair);
-  double* r = rec + (size_t)g * kRec;
-  if (n < S) {
-    r[51] = 0.0;
-    if (idx_out)
-      for (int k = 0; k < S; ++k) idx_out[(size_t)g * S + k] = -1;
-    return;
-  }
-  const double* c = cdf + pts.off[pair];
+__device__ __forceinline__ void draw_sample(const double* __restrict__ c, int n, unsigned long long seed, int g, int (&idx)[S]) {
   const double total = c[n - 1];
   Philox rng{(uint32_t)seed, (uint32_t)(seed >> 32)};
-  int idx[S];
   uint32_t u4[4];
   int blk = 0, used = 4;
   for (int k = 0; k < S; ++k) {
@@ -748,6 +736,25 @@ __global__ void __launch_bounds__(128) ransac_sample_kernel(RaggedPts pts, int P
     }
     idx[k] = pick;
   }
+}
+
+template <int S>
+__global__ void __launch_bounds__(128) ransac_sample_kernel(RaggedPts pts, int P, int H, const double* __restrict__ cdf,
+                                                            unsigned long long seed, double* __restrict__ rec,
+                                                            int* __restrict__ idx_out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P * H) return;
+  const int pair = g / H;
+  const int n = pts.count(pair);
+  double* r = rec + (size_t)g * kRec;
+  if (n < S) {
+    r[51] = 0.0;
+    if (idx_out)
+      for (int k = 0; k < S; ++k) idx_out[(size_t)g * S + k] = -1;
+    return;
+  }
+  int idx[S];
+  draw_sample<S>(cdf + pts.off[pair], n, seed, g, idx);
   if (idx_out)
     for (int k = 0; k < S; ++k) idx_out[(size_t)g * S + k] = idx[k];
   // the moment record of eightpt_accumulate_kernel for these S correspondences, unit weights (:253 passes ones)
@@ -784,6 +791,70 @@ __global__ void __launch_bounds__(128) ransac_sample_kernel(RaggedPts pts, int P
   r[51] = (double)S;
 }
 
+
+// The recipe's model type (`essential_cv2`: a 5-point solver on 6 sampled correspondences, ransac.py:250-253 with
+// cv_geometry.py:836-859 / the in-tree batched 5-point :861-1041): one thread per (pair, hypothesis) draws 6 distinct
+// correspondences, solves Nister's 5-point on the first five (fivept.cuh, up to 10 essential matrices) and keeps the
+// candidate with the smallest squared Sampson distance at the sixth -- one model per hypothesis, so the scoring step is
+// the same as for the 8-point models.  Writes E row-major (unit Frobenius norm), zeros when there is no solution.
+__global__ void __launch_bounds__(64) ransac_sample5_kernel(RaggedPts pts, int P, int H, const double* __restrict__ cdf,
+                                                            unsigned long long seed, float* __restrict__ models,
+                                                            int* __restrict__ idx_out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P * H) return;
+  const int pair = g / H;
+  const int n = pts.count(pair);
+  float* out = models + (size_t)g * 9;
+  if (n < 8) {   // the scoring step treats pairs with fewer than 8 correspondences as unsolved (same bound as the 8-point mode)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[k] = 0.f;
+    if (idx_out)
+      for (int k = 0; k < 6; ++k) idx_out[(size_t)g * 6 + k] = -1;
+    return;
+  }
+  int idx[6];
+  draw_sample<6>(cdf + pts.off[pair], n, seed, g, idx);
+  if (idx_out)
+    for (int k = 0; k < 6; ++k) idx_out[(size_t)g * 6 + k] = idx[k];
+  double X1[6], Y1[6], X2[6], Y2[6];
+  for (int k = 0; k < 6; ++k) {
+    float a, b, c, d, w;
+    pts.load(pair, idx[k], a, b, c, d, w);
+    X1[k] = a; Y1[k] = b; X2[k] = c; Y2[k] = d;
+  }
+  double Es[10][9];
+  const int ns = fivept::solve(X1, Y1, X2, Y2, Es);
+  int best = -1;
+  double best_err = 1e300;
+  for (int q = 0; q < ns; ++q) {
+    const double* E = Es[q];
+    const double lx = E[0] * X1[5] + E[1] * Y1[5] + E[2], ly = E[3] * X1[5] + E[4] * Y1[5] + E[5],
+                 lz = E[6] * X1[5] + E[7] * Y1[5] + E[8];
+    const double mx = E[0] * X2[5] + E[3] * Y2[5] + E[6], my = E[1] * X2[5] + E[4] * Y2[5] + E[7];
+    const double num = X2[5] * lx + Y2[5] * ly + lz;
+    const double err = num * num / (lx * lx + ly * ly + mx * mx + my * my);
+    if (err < best_err) { best_err = err; best = q; }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) out[k] = best >= 0 ? (float)Es[best][k] : 0.f;
+}
+
+// diagnostics / tests: all solutions of the 5-point solver for explicit minimal samples.  pts [S,5,4] = (x1, y1, x2, y2)
+// calibrated, fp64; E [S,10,9]; nsol [S]
+__global__ void fivept_solve_kernel(const double* __restrict__ pts5, int S, double* __restrict__ E, int* __restrict__ nsol) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double x1[5], y1[5], x2[5], y2[5];
+  for (int k = 0; k < 5; ++k) {
+    x1[k] = pts5[(s * 5 + k) * 4]; y1[k] = pts5[(s * 5 + k) * 4 + 1];
+    x2[k] = pts5[(s * 5 + k) * 4 + 2]; y2[k] = pts5[(s * 5 + k) * 4 + 3];
+  }
+  double Es[10][9];
+  const int ns = fivept::solve(x1, y1, x2, y2, Es);
+  nsol[s] = ns;
+  for (int q = 0; q < 10; ++q)
+    for (int k = 0; k < 9; ++k) E[((size_t)s * 10 + q) * 9 + k] = q < ns ? Es[q][k] : 0.0;
+}
 }  // namespace far
 
 using namespace far;
@@ -895,8 +966,8 @@ extern "C" int far_ransac_sample_models(const float* mkpts0, const float* mkpts1
                                         float* models, int* sample_idx, float* workspace, size_t workspace_bytes,
                                         void* stream) {
   if (P <= 0 || H <= 0) return FAR_OK;
-  FAR_REQUIRE(offsets && K0 && K1 && models && workspace && sample_size == 8 && (M == 0 || (mkpts0 && mkpts1)) &&
-              (prior_rt == nullptr || bias_sigma_sq > 0.f));
+  FAR_REQUIRE(offsets && K0 && K1 && models && workspace && (sample_size == 8 || sample_size == 6) &&
+              (M == 0 || (mkpts0 && mkpts1)) && (prior_rt == nullptr || bias_sigma_sq > 0.f));
   if (workspace_bytes < far_ransac_sample_models_workspace_bytes(M, P, H)) return FAR_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
@@ -906,9 +977,22 @@ extern "C" int far_ransac_sample_models(const float* mkpts0, const float* mkpts1
   ProfScope prof(PROF_SOLVER, 0.0, 0.0, st);
   ransac_cdf_kernel<<<P, 256, 0, st>>>(pts, P, prior_rt, bias_sigma_sq, cdf);
   FAR_CHECK_LAUNCH();
+  if (sample_size == 6) {   // 5-point minimal solver + one disambiguating correspondence
+    ransac_sample5_kernel<<<ceil_div(P * H, 64), 64, 0, st>>>(pts, P, H, cdf, seed, models, sample_idx);
+    FAR_CHECK_LAUNCH();
+    return FAR_OK;
+  }
   ransac_sample_kernel<8><<<ceil_div(P * H, 128), 128, 0, st>>>(pts, P, H, cdf, seed, rec, sample_idx);
   FAR_CHECK_LAUNCH();
   eightpt_solve_kernel<<<ceil_div(P * H, 64), 64, 0, st>>>(rec, P * H, models);
+  FAR_CHECK_LAUNCH();
+  return FAR_OK;
+}
+
+extern "C" int far_five_point(const double* pts5, int S, double* E, int* nsol, void* stream) {
+  if (S <= 0) return FAR_OK;
+  FAR_REQUIRE(pts5 && E && nsol);
+  fivept_solve_kernel<<<ceil_div(S, 64), 64, 0, (cudaStream_t)stream>>>(pts5, S, E, nsol);
   FAR_CHECK_LAUNCH();
   return FAR_OK;
 }

@@ -465,21 +465,41 @@ def segment_offsets(m_bids, P):
     return off
 
 
-def ransac_sample_models(mkpts0, mkpts1, offsets, K0, K1, prior_rt, bias_sigma_sq, H, seed, return_indices=False):
+def five_point(pts5):
+    """Nister's 5-point solver (cv_geometry.py:861-1041) for explicit minimal samples: pts5 [S,5,4] fp64 calibrated
+    (x1, y1, x2, y2) -> (E [S,10,3,3] fp64 with x2h^T E x1h = 0, zero padded; nsol [S] int32)."""
+    lib = L.load()
+    if not pts5.is_cuda:
+        raise FarError("far_b200 ops need CUDA tensors")
+    p = pts5.to(torch.float64).contiguous()
+    S = p.shape[0]
+    E = torch.empty((S, 10, 3, 3), dtype=torch.float64, device=p.device)
+    ns = torch.empty(S, dtype=torch.int32, device=p.device)
+    check(lib.far_five_point(ptr(p), S, ptr(E), ptr(ns), stream()), "far_five_point")
+    return E, ns
+
+
+def ransac_sample_models(mkpts0, mkpts1, offsets, K0, K1, prior_rt, bias_sigma_sq, H, seed, return_indices=False,
+                         minimal_solver="8pt"):
     """RANSAC.sample + estimate_model_from_minsample (third_party/prior_ransac/ransac.py:161-175,250-253,358-367) for a
-    ragged batch: H minimal 8-point models per pair from (prior-biased or uniform) samples drawn on the device with a
-    counter-based Philox generator.  Returns models [P,H,3,3] (and sample indices [P,H,8] int32)."""
+    ragged batch: H minimal models per pair from (prior-biased or uniform) samples drawn on the device with a
+    counter-based Philox generator.  minimal_solver '8pt': the normalised 8-point on 8 draws; '5pt': the recipe's model
+    type, Nister's 5-point on 5 draws disambiguated by a sixth.  Returns models [P,H,3,3] (and sample indices
+    [P,H,8 or 6] int32)."""
     lib = L.load()
     P = offsets.shape[0] - 1
     dev = offsets.device
     M = int(mkpts0.shape[0])
+    if minimal_solver not in ("8pt", "5pt"):
+        raise FarError(f"unknown minimal solver {minimal_solver!r}")
+    S = 8 if minimal_solver == "8pt" else 6
     models = torch.empty((P, H, 3, 3), dtype=torch.float32, device=dev)
-    idx = torch.empty((P, H, 8), dtype=torch.int32, device=dev) if return_indices else None
+    idx = torch.empty((P, H, S), dtype=torch.int32, device=dev) if return_indices else None
     pr = f32c(prior_rt) if prior_rt is not None else None
     ws = _ws(lib.far_ransac_sample_models_workspace_bytes(M, P, H), dev)
     with _timed("far_ransac_sample_models"):
         check(lib.far_ransac_sample_models(ptr(f32c(mkpts0)), ptr(f32c(mkpts1)), ptr(offsets), M, P, ptr(f32c(K0)),
-                                           ptr(f32c(K1)), ptr(pr), float(bias_sigma_sq), H, 8,
+                                           ptr(f32c(K1)), ptr(pr), float(bias_sigma_sq), H, S,
                                            int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(models), ptr(idx), ptr(ws), ws.numel(),
                                            stream()), "far_ransac_sample_models")
     return (models, idx) if return_indices else models

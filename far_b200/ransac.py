@@ -13,9 +13,11 @@ What `estimate_pose(..., solver='prior_ransac', priorRT=...)` does for ONE pair 
 here runs for all pairs of the batch at once, entirely on the device, as THREE C-ABI calls with no torch math and no
 host synchronisation in between:
 
-    far_ransac_sample_models   bias weights + per-pair CDF + Philox inverse-CDF sampling + the in-repo normalised
-                               8-point on each 8-sample (the recipe's `essential_cv2` model calls OpenCV's 5-point
-                               solver 2048 times per pair on the CPU -- un-vendored arithmetic)
+    far_ransac_sample_models   bias weights + per-pair CDF + Philox inverse-CDF sampling + the minimal solver: the
+                               in-repo normalised 8-point on each 8-sample (default), or -- the recipe's model type,
+                               `essential_cv2` = OpenCV's 5-point on 6 points, 2048 CPU calls per pair there -- Nister's
+                               5-point on 5 + 1 draws (minimal_solver='5pt'; csrc/fivept.cuh restates the in-tree
+                               batched 5-point cv_geometry.py:861-1041; OpenCV's own arithmetic is un-vendored)
     far_prior_ransac_score     prior score, Sampson inliers, argmax, masks and the 3 counters
     far_pose_from_essential    cheirality vote over the inliers (cv2.recoverPose's criterion)
 
@@ -52,8 +54,9 @@ def normalise_prior(prior_rt):
 
 @torch.no_grad()
 def ransac_round(mkpts0, mkpts1, m_bids, K0, K1, prior_rt=None, batch_size=2048, inl_th=3e-7, prior_lambda=0.3,
-                 bias_sigma_sq=0.1, biased=True, pcl=None, seed=0, offsets=None):
-    """One (prior-guided) RANSAC round for every pair of a ragged batch.  mkpts* [M,2] pixel keypoints, m_bids [M]
+                 bias_sigma_sq=0.1, biased=True, pcl=None, seed=0, offsets=None, minimal_solver="8pt"):
+    """One (prior-guided) RANSAC round for every pair of a ragged batch.  minimal_solver: '8pt' (default: the in-repo
+    normalised 8-point) or '5pt' (the recipe's model type: Nister's 5-point on 5 + 1 draws, ops.ransac_sample_models).  mkpts* [M,2] pixel keypoints, m_bids [M]
     sorted pair ids, K0/K1 [N,3,3], prior_rt [N,3,4] or None.  Returns a dict of device tensors:
     Rt [N,3,4], E [N,3,3], mask [M] uint8 (bit 0 inlier / 1 tight / 2 ultra tight), counts3 [N,3] int32, best [N],
     scores [N,H], counts [N] (matches per pair), n_pos [N]."""
@@ -66,7 +69,7 @@ def ransac_round(mkpts0, mkpts1, m_bids, K0, K1, prior_rt=None, batch_size=2048,
         mkpts0 = mkpts1 = torch.zeros(1, 2, device=dev)
     prior = prior_rt.to(dev).float().contiguous() if prior_rt is not None else None
     models = ops.ransac_sample_models(mkpts0, mkpts1, offsets, K0, K1, prior if biased else None, bias_sigma_sq,
-                                      batch_size, seed)
+                                      batch_size, seed, minimal_solver=minimal_solver)
     if prior is not None and pcl is None:
         pcl = default_pcl(dev)
     scores, best, best_E, counts3, mask = ops.prior_ransac_score(mkpts0, mkpts1, offsets, K0, K1, models, prior, pcl,
@@ -78,13 +81,13 @@ def ransac_round(mkpts0, mkpts1, m_bids, K0, K1, prior_rt=None, batch_size=2048,
 
 @torch.no_grad()
 def prior_ransac_round(data, K0, K1, prior_rt, batch_size=2048, inl_th=3e-7, prior_lambda=0.3, bias_sigma_sq=0.1,
-                       biased=True, pcl=None, seed=0):
+                       biased=True, pcl=None, seed=0, minimal_solver="8pt"):
     """The round applied to a LoFTR `data` dict: reads m_bids, mkpts0_f, mkpts1_f; prior_rt [N,3,4] (e.g. the FAR
     head's prediction, loftr.py:187-192) or None for the reference's `prior_ransac_noprior` round.  Writes the keys
     spvs_RT writes (supervision.py:226-233: loftr_rt, num_correspondences*, inliers_best_tight / ultra_tight) with the
     reference's meaning -- `num_correspondences_after_ransac` IS the RANSAC inlier count -- and returns loftr_rt."""
     r = ransac_round(data['mkpts0_f'], data['mkpts1_f'], data['m_bids'], K0, K1, prior_rt, batch_size, inl_th,
-                     prior_lambda, bias_sigma_sq, biased, pcl, seed)
+                     prior_lambda, bias_sigma_sq, biased, pcl, seed, minimal_solver=minimal_solver)
     off = r['offsets']
     c3 = r['counts3'].to(torch.int64)
     data.update({'loftr_rt': r['Rt'], 'expec_rt': r['Rt'], 'expec_e': r['E'], 'ransac_inlier_mask': r['mask'],

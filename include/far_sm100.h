@@ -237,7 +237,7 @@ int far_prior_ransac_score(const float* mkpts0, const float* mkpts1, const long 
 /* ---- prior-guided RANSAC round, sampling + minimal solver (no eager-torch math, no host sync) -----------------------
  * far_segment_offsets: m_bids [M] int64, sorted ascending (what get_coarse_match yields, coarse_matching.py:193) ->
  *   offsets [P+1] int64 with offsets[b] = first match of pair b (replaces bincount + cumsum).
- * far_ransac_sample_models: for every pair p and hypothesis h < H draws `sample_size` (= 8) correspondences of the
+ * far_ransac_sample_models: for every pair p and hypothesis h < H draws `sample_size` (8, or 6: below) correspondences of the
  *   pair's segment and solves the minimal model with the in-repo normalised 8-point (cv_geometry.py:772-833, unit
  *   weights as ransac.py:250-253) -> models [P,H,3,3].  Sampling distribution (ransac.py:161-175, :358-367):
  *     prior_rt != NULL: p_i ~ exp(-symmetrical_epipolar_distance(x0_i, x1_i, [t]_x R) / bias_sigma_sq) + 1e-4 with the
@@ -248,8 +248,15 @@ int far_prior_ransac_score(const float* mkpts0, const float* mkpts1, const long 
  *   times).  The reference uses numpy's global RNG there, so only the distribution is the contract; the counter-based
  *   generator makes samples reproducible and testable.  sample_idx [P,H,8] int32 (segment-local; -1 for pairs with
  *   fewer than 8 matches) may be NULL.  Pairs with < 8 matches get all-zero models (rejected by the scoring step).
- *   The recipe of record's minimal solver is OpenCV's 5-point through cv2.findEssentialMat(LMEDS) on 6 points
- *   (cv_geometry.py:836-859), un-vendored arithmetic: the in-repo 8-point is the minimal solver here. */
+ *   sample_size == 6 selects the recipe's model type instead (`essential_cv2`: a 5-point solver on 6 sampled points,
+ *   ransac.py:250-253 / cv_geometry.py:836-859): Nister's 5-point (the in-tree batched version cv_geometry.py:861-1041,
+ *   restated in csrc/fivept.cuh) on the first five draws, the candidate with the smallest squared Sampson distance at
+ *   the sixth is the hypothesis' model (E with unit Frobenius norm); sample_idx is then [P,H,6].  OpenCV's own 5-point
+ *   arithmetic is un-vendored, so that mode is pinned to the restated algorithm, not to cv2.
+ * far_five_point: every real solution of the 5-point solver for S explicit minimal samples (tests / diagnostics):
+ *   pts5 [S,5,4] fp64 calibrated (x1, y1, x2, y2) -> E [S,10,9] fp64 row-major with x2h^T E x1h = 0 (zero padded),
+ *   nsol [S]. */
+int far_five_point(const double* pts5, int S, double* E, int* nsol, void* stream);
 int far_segment_offsets(const long long* m_bids, long long M, int P, long long* offsets, void* stream);
 size_t far_ransac_sample_models_workspace_bytes(long long M, int P, int H);
 int far_ransac_sample_models(const float* mkpts0, const float* mkpts1, const long long* offsets, long long M, int P,

@@ -472,7 +472,7 @@ def test_vitess_batch64_matches_per_sample():
             pos = O.emm_positional_encodings_vit(intr[b0:b0 + 1])
             to, Ro, r6o, wto = O.vit_fusion_head(sd, feats[2 * b0:2 * b0 + 2], pos, lp[b0:b0 + 1], nc[b0:b0 + 1], mean, std)
             assert_close(full[b0:b0 + 1, 3:], r6o, 1e-4, 1e-4, f"sample {b0}: normalised 6-D rotation vs oracle")
-            assert_close(full[b0:b0 + 1, :3] * std[:3] + mean[:3], to, 1e-4, 1e-4, f"sample {b0}: translation vs oracle")
+            assert_close(full[b0:b0 + 1, :3].cpu() * std[:3] + mean[:3], to, 1e-4, 1e-4, f"sample {b0}: translation vs oracle")
             assert_close(wt[b0:b0 + 1], wto, 1e-4, 1e-4, f"sample {b0}: gate vs oracle")
 
 

@@ -251,3 +251,94 @@ def test_pipeline_with_prior_ransac_round_runs():
     assert out["data"]["ransac_scores"].shape == (2, 512)
     R = out["loftr_rt"][:, :, :3].double().cpu()
     assert (R @ R.transpose(1, 2) - torch.eye(3, dtype=torch.float64)).abs().max() < 1e-4
+
+
+def _five_point_samples(S, seed):
+    """S minimal samples (5 calibrated correspondences) of random two-view geometry, exact (no noise)."""
+    p1, p2, _, R, t = synth.two_view_geometry(S, 5, seed=seed, noise=0.0, outlier_frac=0.0)
+    return torch.cat([p1, p2], -1).double(), R, t
+
+
+def _set_distance(Ea, Eb):
+    """max over the matrices of Ea of the distance (up to sign, unit Frobenius norm) to the closest matrix of Eb."""
+    if len(Ea) == 0:
+        return 0.0
+    if len(Eb) == 0:
+        return float("inf")
+    a = np.stack([e.reshape(-1) / np.linalg.norm(e) for e in Ea])
+    b = np.stack([e.reshape(-1) / np.linalg.norm(e) for e in Eb])
+    d = np.minimum(np.linalg.norm(a[:, None] - b[None], axis=-1), np.linalg.norm(a[:, None] + b[None], axis=-1))
+    return float(d.min(1).max())
+
+
+def test_five_point_solver_vs_oracle():
+    """csrc/fivept.cuh (Nister 5-point, one thread per sample) against oracle.run_5point_nister (the numpy restatement of
+    cv_geometry.py:861-1041) on 256 exact minimal samples: the same SET of real solutions (up to sign), every solution
+    satisfies the five epipolar equations, the trace constraint and det E = 0, and one of them is the true E."""
+    S = 256
+    pts, R, t = _five_point_samples(S, 31)
+    E, ns = ops.five_point(cu(pts))
+    E, ns = E.cpu().numpy(), ns.cpu().numpy()
+    assert ns.min() >= 1 and ns.max() <= 10
+    mismatched = 0
+    for s in range(S):
+        p = pts[s].numpy()
+        Eo = O.run_5point_nister(p[:, :2], p[:, 2:])
+        Eg = E[s, :ns[s]]
+        x1 = np.concatenate([p[:, :2], np.ones((5, 1))], 1)
+        x2 = np.concatenate([p[:, 2:], np.ones((5, 1))], 1)
+        for e in Eg:
+            assert abs(np.linalg.norm(e) - 1.0) < 1e-9
+            assert np.abs(np.einsum("ni,ij,nj->n", x2, e, x1)).max() < 1e-8, "epipolar equations of the sample"
+            assert abs(np.linalg.det(e)) < 1e-8
+            assert np.abs(e @ e.T @ e - 0.5 * np.trace(e @ e.T) * e).max() < 1e-8, "trace constraint"
+        tx = np.array([[0, -t[s, 2], t[s, 1]], [t[s, 2], 0, -t[s, 0]], [-t[s, 1], t[s, 0], 0]], dtype=np.float64)
+        Et = tx @ R[s].double().numpy()
+        assert _set_distance([Et], Eg) < 1e-6, f"sample {s}: the true essential matrix is among the solutions"
+        # same solution set as the oracle; a pair of nearly coincident real roots may be classified differently by the
+        # two root finders (companion-matrix eigenvalues vs Aberth iteration): counted, must be rare
+        if len(Eo) != len(Eg) or _set_distance(Eo, Eg) > 1e-6 or _set_distance(Eg, Eo) > 1e-6:
+            mismatched += 1
+    print(f"[five_point] samples whose real-root set differs from the oracle's: {mismatched} / {S}")
+    assert mismatched <= S // 50
+
+
+def test_ransac_round_five_point_minimal_solver():
+    """The round with the recipe's model type (5-point on 5 + 1 draws): sampling contract (6 distinct Philox draws,
+    bit-equal to the numpy restatement), every hypothesis' model is an exact solution for its first five draws, and the
+    round recovers the true pose of a ragged batch with 30 % outliers."""
+    sizes = [900, 5, 400, 1300]
+    mk0, mk1, bids, K, Rs, ts = _pixel_pairs(sizes)
+    off = ops.segment_offsets(cu(bids), len(sizes))
+    H = 512
+    models, idx = ops.ransac_sample_models(cu(mk0), cu(mk1), off, cu(K), cu(K), None, 0.1, H, 5, return_indices=True,
+                                           minimal_solver="5pt")
+    models, idx = models.cpu(), idx.cpu()
+    assert idx.shape == (4, H, 6) and (idx[1] == -1).all() and (models[1] == 0).all()
+    for b in (0, 2, 3):
+        ref = O.ransac_sample_indices(np.ones(sizes[b]), H, 5, pair=b, S=6)
+        assert np.array_equal(idx[b].numpy().astype(np.int64), ref), f"pair {b}: Philox draws"
+        assert all(len(set(row.tolist())) == 6 for row in idx[b])
+    # K-normalised points of pair 0; each model satisfies the epipolar equation of its own first five draws
+    o0 = int(off[0])
+    x0 = (mk0[o0:o0 + sizes[0]] - K[0, :2, 2]) / torch.stack([K[0, 0, 0], K[0, 1, 1]])
+    x1 = (mk1[o0:o0 + sizes[0]] - K[0, :2, 2]) / torch.stack([K[0, 0, 0], K[0, 1, 1]])
+    solved = 0
+    for h in range(H):
+        Em = models[0, h].double()
+        if Em.abs().max() == 0:
+            continue
+        solved += 1
+        sel = idx[0, h, :5].long()
+        a = torch.cat([x0[sel], torch.ones(5, 1)], 1).double()
+        b = torch.cat([x1[sel], torch.ones(5, 1)], 1).double()
+        assert torch.einsum("ni,ij,nj->n", b, Em, a).abs().max() < 1e-5, h     # fp32 model, fp32 pixel keypoints
+    assert solved >= 0.98 * H
+    data = {"mkpts0_f": cu(mk0), "mkpts1_f": cu(mk1), "m_bids": cu(bids)}
+    Rt = prior_ransac_round(data, cu(K), cu(K), None, batch_size=1024, inl_th=3e-7 * 1e3, seed=1, minimal_solver="5pt").cpu()
+    for b in (0, 2, 3):
+        cosang = ((Rt[b, :, :3].T @ Rs[b]).trace() - 1) / 2
+        assert torch.rad2deg(torch.arccos(cosang.clamp(-1, 1))) < 6.0, f"pair {b}: rotation error"
+        n_in = int(data["num_correspondences_after_ransac"][b])
+        assert 0.6 * sizes[b] <= n_in <= 0.75 * sizes[b], (b, n_in)
+    assert torch.equal(Rt[1], torch.eye(3, 4))
