@@ -178,7 +178,7 @@ class RANSAC(torch.nn.Module):
     def __init__(self, model_type='homography', inl_th=2.0, batch_size=2048, max_iter=10, confidence=0.99,
                  max_lo_iters=5, prior_params={}, use_noexp_prior_scoring=False, use_linear_bias_sampling=False,
                  bias_sigma_sq=1.0, compute_stopping_inlier_only=False, perform_early_stopping=False, l1_dist=False,
-                 use_epipolar_error=False, K=None, normalize=False, seed=0):
+                 use_epipolar_error=False, K=None, normalize=False, seed=0, minimal_solver=None):
         super().__init__()
         if model_type not in ('essential_cv2', 'essential', 'fundamental'):
             raise NotImplementedError(f"{model_type}: only the essential/fundamental models are on the FAR path")
@@ -192,7 +192,14 @@ class RANSAC(torch.nn.Module):
         self.bias_sigma_sq, self.prior_params, self.seed = bias_sigma_sq, prior_params, seed
         self.use_prior = bool(prior_params)
         self.prior_lambda = prior_params['lambda'] if self.use_prior else 1.0
-        self.minimal_sample_size = 8
+        # minimal solver of a hypothesis: the in-repo normalised 8-point on 8 draws (default for every model type: fastest),
+        # or '5pt' = the sample sizes of the reference's essential models (ransac.py:146-157: `essential` 5 draws,
+        # `essential_cv2` 6): Nister's 5-point on 5 + 1 draws (csrc/fivept.cuh).  FAR_RANSAC_MINIMAL=5pt selects it globally.
+        import os
+        self.minimal_solver = minimal_solver or os.environ.get("FAR_RANSAC_MINIMAL", "8pt")
+        if self.minimal_solver not in ("8pt", "5pt") or (self.minimal_solver == "5pt" and model_type == "fundamental"):
+            raise NotImplementedError(f"minimal_solver={self.minimal_solver!r} for model_type={model_type!r}")
+        self.minimal_sample_size = 8 if self.minimal_solver == "8pt" else 6
 
     def forward(self, kp1, kp2, weights=None):
         from .ransac import ransac_round
@@ -209,7 +216,7 @@ class RANSAC(torch.nn.Module):
             biased = self.use_prior and i % 2 == 0 and bool(self.prior_params.get('biased_sampling'))   # :375-378
             r = ransac_round(kp1.float(), kp2.float(), bids, eyeK, eyeK, prior, batch_size=self.batch_size,
                              inl_th=self.inl_th, prior_lambda=self.prior_lambda, bias_sigma_sq=self.bias_sigma_sq,
-                             biased=biased, pcl=pcl, seed=self.seed + i)
+                             biased=biased, pcl=pcl, seed=self.seed + i, minimal_solver=self.minimal_solver)
             b = int(r['best'][0])
             if b >= 0 and float(r['scores'][0, b]) > best_score:
                 best_score, out = float(r['scores'][0, b]), r

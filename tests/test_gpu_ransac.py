@@ -342,3 +342,17 @@ def test_ransac_round_five_point_minimal_solver():
         n_in = int(data["num_correspondences_after_ransac"][b])
         assert 0.6 * sizes[b] <= n_in <= 0.75 * sizes[b], (b, n_in)
     assert torch.equal(Rt[1], torch.eye(3, 4))
+
+
+def test_ransac_shim_five_point_model_type():
+    """RANSAC('essential_cv2', minimal_solver='5pt').forward on K-normalised keypoints: the recipe's model type end to end."""
+    mk0, mk1, bids, K, Rs, ts = _pixel_pairs([700], outlier_frac=0.25)
+    f, c = K[0, 0, 0], K[0, :2, 2]
+    kp1, kp2 = (mk0 - c) / f, (mk1 - c) / f
+    r = fsolver.RANSAC('essential_cv2', inl_th=3e-4, batch_size=1024, max_iter=2, max_lo_iters=0, minimal_solver='5pt', seed=3)
+    assert r.minimal_sample_size == 6
+    E, inl, tight, ultra = r(cu(kp1), cu(kp2))
+    assert E.shape == (3, 3) and 0.6 * 700 <= int(inl.sum()) <= 0.8 * 700
+    assert int(tight.sum()) <= int(inl.sum()) and int(ultra.sum()) <= int(tight.sum())
+    tx = torch.tensor([[0, -ts[0][2], ts[0][1]], [ts[0][2], 0, -ts[0][0]], [-ts[0][1], ts[0][0], 0]])
+    assert f_distance(E[None].cpu(), (tx @ Rs[0])[None]).max() < 0.05
