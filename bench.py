@@ -142,7 +142,8 @@ class Mp3dLoftrFar(Workload):
         self.img = synth.synth_pair_images(self.units, seed=20240002 + rank)
         K = synth.mp3d_intrinsics(self.units).to(dev)
         self.pipe = FarPosePipeline(self.model, K, K, prior_ransac=not self.args.no_prior_ransac,
-                                    first_solver=self.args.first_solver, graph=not self.args.no_graph)
+                                    first_solver=self.args.first_solver, graph=not self.args.no_graph,
+                                    ransac_kwargs={"minimal_solver": self.args.minimal_solver})
         self.nmatch = None
 
     def host_inputs(self):
@@ -170,6 +171,8 @@ class Mp3dLoftrFar(Workload):
                 if a.first_solver == "ransac" else "mconf-weighted 8-point + cheirality (SURVEY 8d config 2 literal)",
                 "second_solver_call": "prior-guided RANSAC round on the GPU (2048 hypotheses/pair)"
                 if not a.no_prior_ransac else "same as the first call",
+                "ransac_minimal_solver": "in-repo normalised 8-point on 8 draws" if a.minimal_solver == "8pt" else
+                "Nister 5-point on 5 + 1 draws (the recipe's essential_cv2 sample size)",
                 "head_trunk": "evaluated once per forward and reused by the 2nd head invocation (identical outputs; "
                               "--no-trunk-reuse re-evaluates it)" if not a.no_trunk_reuse else
                               "re-evaluated by each of the 2 head invocations",
@@ -785,6 +788,9 @@ def main():
     ap.add_argument("--first-solver", default="ransac", choices=["ransac", "weighted_8pt"],
                     help="mp3d_loftr_far: first solver call = GPU RANSAC round (default; counters are inlier counts) or "
                          "the single mconf-weighted 8-point fit")
+    ap.add_argument("--minimal-solver", default="8pt", choices=["8pt", "5pt"],
+                    help="mp3d_loftr_far: minimal solver of the RANSAC rounds (5pt = the recipe's model type, Nister 5-point "
+                         "on 5 + 1 draws; default the in-repo 8-point)")
     ap.add_argument("--no-prior-ransac", action="store_true",
                     help="mp3d_loftr_far: re-run the first solver between the two head invocations instead of the "
                          "prior-guided RANSAC round (far_b200/ransac.py, 2048 hypotheses per pair)")
