@@ -73,7 +73,7 @@ __device__ inline int real_roots_deg10(const double* c, double* roots) {
     zr[k] = r0 * cos(ang) * (1.0 + 0.02 * k);
     zi[k] = r0 * sin(ang) * (1.0 + 0.02 * k);
   }
-  for (int it = 0; it < 300; ++it) {
+  for (int it = 0; it < 64; ++it) {   // typically 15-25 iterations; the Gauss-Newton polish in solve() restores the last digits
     double maxstep = 0.0;
     for (int k = 0; k < deg; ++k) {
       // Horner for p and p' at z_k
@@ -104,7 +104,7 @@ __device__ inline int real_roots_deg10(const double* c, double* roots) {
       zr[k] -= stepr; zi[k] -= stepi;
       maxstep = fmax(maxstep, (fabs(stepr) + fabs(stepi)) / (1.0 + fabs(zr[k]) + fabs(zi[k])));
     }
-    if (maxstep < 4e-16) break;
+    if (maxstep < 1e-12) break;
   }
   int n = 0;
   for (int k = 0; k < deg; ++k) {
