@@ -149,6 +149,29 @@ class Mp3dLoftrFar(Workload):
     def host_inputs(self):
         return [t.pin_memory() for t in self.img]
 
+    def parity_check(self):
+        """Outside the timed region: the benchmarked model (same seed-1234 weights as the fixture) on the fixture's
+        image pair, match set against tests/golden/loftr_full.npz (produced by the unmodified reference on the CPU)."""
+        import numpy as np
+        from far_b200 import synth
+        path = os.path.join(ROOT, "tests", "golden", "loftr_full.npz")
+        if not os.path.exists(path):
+            return None
+        gold = np.load(path)
+        img0, img1 = synth.synth_pair_images(1, seed=int(gold["seed"][1]))
+        data = {"image0": img0.to(self.dev), "image1": img1.to(self.dev)}
+        with torch.no_grad():
+            self.model(data)
+        got = {tuple(r) for r in torch.stack([data[k] for k in ("b_ids", "i_ids", "j_ids")], 1).cpu().tolist()}
+        ref = {tuple(r) for r in np.stack([gold[k] for k in ("b_ids", "i_ids", "j_ids")], 1).astype(np.int64).tolist()}
+        ordered = [tuple(r) for r in torch.stack([data[k] for k in ("b_ids", "i_ids", "j_ids")], 1).cpu().tolist()] == \
+            [tuple(r) for r in np.stack([gold[k] for k in ("b_ids", "i_ids", "j_ids")], 1).astype(np.int64).tolist()]
+        common = min(len(data["mkpts1_f"]), len(gold["mkpts1_f"])) if ordered else 0
+        dpx = float((data["mkpts1_f"].cpu()[:common] - torch.from_numpy(gold["mkpts1_f"])[:common]).abs().max()) if common else None
+        return {"fixture": "tests/golden/loftr_full.npz (unmodified reference, CPU, one 640x480 pair)",
+                "matches_reference": len(ref), "matches_far": len(got), "lost": len(ref - got), "spurious": len(got - ref),
+                "identical_ordered_indices": bool(ordered), "max_abs_mkpts1_f_px": dpx}
+
     def step(self, inp):
         out = self.pipe(inp[0], inp[1])
         self.nmatch = out["num_matches"]
@@ -751,6 +774,11 @@ def run_far(args, rank, world, local_rank):
                       "max": float(per_rank[:, 0].max()) / args.steps},
             "e2e": {"min": float(per_rank[:, 1].min()) / args.steps, "median": float(per_rank[:, 1].median()) / args.steps,
                     "max": float(per_rank[:, 1].max()) / args.steps}}
+    if world == 1 and hasattr(wl, "parity_check"):
+        try:   # near-tie flips of the match set against the reference fixture, recorded in the line
+            line["near_tie_flips"] = wl.parity_check()
+        except Exception as ex:
+            line["near_tie_flips"] = {"error": repr(ex)[:300]}
     if world == 1 and not args.no_gpu_eager_baseline:
         try:
             fn, n = wl.eager_setup(dev)
