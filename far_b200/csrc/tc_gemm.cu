@@ -499,8 +499,8 @@ int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   ProfScope prof(PROF_TC_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)Gb * N * K + (double)M * N), st);
   // raw fp32 activations: the A operand goes through TMEM.  FAR_TC_TS = 1 (default): one CTA per 128 x 128 tile
-  // (tc_gemm_ts.cu); 2: CTA pairs sharing B (tc_gemm_pair.cu: 13 % faster than mode 1 on an idle GPU, 15-20 % slower inside
-  // the power-capped step); 0: the all-shared-memory kernel below
+  // (tc_gemm_ts.cu); 2: CTA pairs sharing B (tc_gemm_pair.cu: 13 % faster than mode 1 at ~1.1 GHz SM clock, 15-30 % slower at
+  // the 1.5-1.7 GHz of the power-capped step); 0: the all-shared-memory kernel below
   static const int ts_mode = getenv("FAR_TC_TS") ? atoi(getenv("FAR_TC_TS")) : 1;
   const int pair_clusters = (rawA && !cross16 && ts_mode >= 2) ? gemm_pair_max_clusters() : 0;
   if (pair_clusters > 0) {
