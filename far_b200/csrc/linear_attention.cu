@@ -157,9 +157,19 @@ __global__ void __launch_bounds__(256) la_small_kernel(const float* __restrict__
 }
 
 // Fine-level variant with coalesced staging: one CTA per window n covers ALL 8 heads (C = 128 floats = one 512-byte row
-// per token), q/k/v rows are staged with float4 loads by the whole CTA, warp h computes head h exactly like
-// la_small_kernel, and the result goes back through shared memory as full rows.  (la_small_kernel reads 64-byte head
-// slices with scalar loads: 1.1 ms per call at 41.8k windows, ~1/3 of the HBM roofline.)
+// per token), q/k/v rows are staged with float4 loads by the whole CTA, warp h computes head h, and the result goes back
+// through shared memory as full rows.  (la_small_kernel reads 64-byte head slices with scalar loads: 1.1 ms per call at
+// 41.8k windows, ~1/3 of the HBM roofline.)
+// The kernel is instruction-issue bound, not HBM bound (2.1 GB in 780 us = 41 % of the HBM peak with ~13 k warp
+// instructions per window), so this version removes instructions: elu(x)+1 as x+1 | ex2.approx (the GEMM epilogue's form)
+// instead of expm1f; Ksum accumulated by the loading threads (a thread always loads the same 4 columns) instead of 8
+// redundant adds per lane per key; the normaliser Z = S / (Q.Ksum + eps) once per (token, head) instead of 8 FMAs per
+// lane per token; rows padded to 132 floats so lane = token accesses spread over the banks; the output overwrites the K
+// tile (dead after the KV pass), so the per-token __syncwarp is gone.
+constexpr int LA_SP = 132;   // padded row pitch (floats)
+__device__ __forceinline__ float fmap_fast(float x, int applied) {
+  return applied ? x : (x > 0.f ? x + 1.f : exp2f(x * 1.4426950408889634f));
+}
 template <int D, int H>
 __global__ void __launch_bounds__(32 * H) la_small_allheads_kernel(const float* __restrict__ q, int ldq,
                                                                    const float* __restrict__ k, int ldk,
@@ -167,68 +177,78 @@ __global__ void __launch_bounds__(32 * H) la_small_allheads_kernel(const float* 
                                                                    float* __restrict__ out, int ldo, int L, int S,
                                                                    int applied, float eps) {
   constexpr int C = D * H, NT = 32 * H, C4 = C / 4;
-  __shared__ __align__(16) float sm[3][LA_SMALL][C];
+  static_assert(NT % C4 == 0, "a thread must always load the same column group");
+  __shared__ __align__(16) float sm[3][LA_SMALL][LA_SP];
+  __shared__ __align__(16) float ksp[H][C];   // per-warp partial sums of the mapped keys
+  __shared__ __align__(16) float ksum_s[C];
   const long long n = blockIdx.x;
   const int t = threadIdx.x, h = t >> 5, lane = t & 31;
   const float invS = 1.f / (float)S;
-  (void)invS;
-  for (int idx = t; idx < L * C4; idx += NT) {
-    const int r = idx / C4, c4 = idx % C4;
+  const int c4 = t % C4, rstep = NT / C4, r0 = t / C4;
+  for (int r = r0; r < L; r += rstep) {
     float4 a = __ldg(reinterpret_cast<const float4*>(q + ((size_t)n * L + r) * ldq) + c4);
-    a.x = fmap(a.x, applied); a.y = fmap(a.y, applied); a.z = fmap(a.z, applied); a.w = fmap(a.w, applied);
+    a.x = fmap_fast(a.x, applied); a.y = fmap_fast(a.y, applied); a.z = fmap_fast(a.z, applied); a.w = fmap_fast(a.w, applied);
     reinterpret_cast<float4*>(&sm[0][r][0])[c4] = a;
   }
-  for (int idx = t; idx < S * C4; idx += NT) {
-    const int r = idx / C4, c4 = idx % C4;
+  float4 ks4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0; r < S; r += rstep) {
     float4 a = __ldg(reinterpret_cast<const float4*>(k + ((size_t)n * S + r) * ldk) + c4);
     float4 b = __ldg(reinterpret_cast<const float4*>(v + ((size_t)n * S + r) * ldv) + c4);
-    a.x = fmap(a.x, applied); a.y = fmap(a.y, applied); a.z = fmap(a.z, applied); a.w = fmap(a.w, applied);
-    b.x /= (float)S; b.y /= (float)S; b.z /= (float)S; b.w /= (float)S;  // values / v_length (:44)
+    a.x = fmap_fast(a.x, applied); a.y = fmap_fast(a.y, applied); a.z = fmap_fast(a.z, applied); a.w = fmap_fast(a.w, applied);
+    b.x *= invS; b.y *= invS; b.z *= invS; b.w *= invS;  // values / v_length (:44)
+    ks4.x += a.x; ks4.y += a.y; ks4.z += a.z; ks4.w += a.w;
     reinterpret_cast<float4*>(&sm[1][r][0])[c4] = a;
     reinterpret_cast<float4*>(&sm[2][r][0])[c4] = b;
+  }
+  reinterpret_cast<float4*>(&ksp[r0][0])[c4] = ks4;   // r0 = t / 32 = this thread's warp: rows r0, r0 + 8, ...
+  __syncthreads();
+  if (t < C) {   // Ksum[c] = sum of the 8 per-warp partials (once per CTA: the kernel is shared-memory-wavefront bound)
+    float a = ksp[0][t];
+#pragma unroll
+    for (int w = 1; w < H; ++w) a += ksp[w][t];
+    ksum_s[t] = a;
   }
   __syncthreads();
   constexpr int G = 32 / D;      // d-groups per warp (D=16 -> 2)
   constexpr int ND = D / G;      // d's per lane: the CONTIGUOUS block [g*ND, g*ND + ND) -> two broadcast LDS.128 per token
-  static_assert(ND == 8, "la_small_allheads_kernel is written for D = 16");
+  static_assert(ND == 8 && rstep == H, "la_small_allheads_kernel is written for D = 16, H = 8");
   const int e = lane % D, g = lane / D, hb = h * D;
-  float kv[ND], ks[ND];
+  // Z for token `lane` of this head: S / (Q[lane, :] . Ksum + eps)   (linear_attention.py:46-48, the S of :44 folded in)
+  float z = 0.f;
+  if (lane < L) {
+    float den = 0.f;
 #pragma unroll
-  for (int i = 0; i < ND; ++i) { kv[i] = 0.f; ks[i] = 0.f; }
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+      const float4 ksum = reinterpret_cast<const float4*>(&ksum_s[hb])[d4];
+      const float4 qq = reinterpret_cast<const float4*>(&sm[0][lane][hb])[d4];
+      den = fmaf(qq.x, ksum.x, den); den = fmaf(qq.y, ksum.y, den); den = fmaf(qq.z, ksum.z, den); den = fmaf(qq.w, ksum.w, den);
+    }
+    z = (float)S / (den + eps);
+  }
+  float kv[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) kv[i] = 0.f;
   for (int s0 = 0; s0 < S; ++s0) {
     const float ve = sm[2][s0][hb + e];
     const float4 ka = *reinterpret_cast<const float4*>(&sm[1][s0][hb + g * ND]);
     const float4 kb = *reinterpret_cast<const float4*>(&sm[1][s0][hb + g * ND + 4]);
-    const float kd[ND] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
-#pragma unroll
-    for (int i = 0; i < ND; ++i) {
-      kv[i] = fmaf(kd[i], ve, kv[i]);
-      ks[i] += kd[i];
-    }
+    kv[0] = fmaf(ka.x, ve, kv[0]); kv[1] = fmaf(ka.y, ve, kv[1]); kv[2] = fmaf(ka.z, ve, kv[2]); kv[3] = fmaf(ka.w, ve, kv[3]);
+    kv[4] = fmaf(kb.x, ve, kv[4]); kv[5] = fmaf(kb.y, ve, kv[5]); kv[6] = fmaf(kb.z, ve, kv[6]); kv[7] = fmaf(kb.w, ve, kv[7]);
   }
+  __syncwarp();   // the K columns of this head are dead from here on (other warps only touch their own columns)
   for (int l = 0; l < L; ++l) {
     const float4 qa = *reinterpret_cast<const float4*>(&sm[0][l][hb + g * ND]);
     const float4 qb = *reinterpret_cast<const float4*>(&sm[0][l][hb + g * ND + 4]);
-    const float qd[ND] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-    float num = 0.f, den = 0.f;
-#pragma unroll
-    for (int i = 0; i < ND; ++i) {
-      num = fmaf(qd[i], kv[i], num);
-      den = fmaf(qd[i], ks[i], den);
-    }
-#pragma unroll
-    for (int o = D; o < 32; o <<= 1) {
-      num += __shfl_xor_sync(0xffffffffu, num, o);
-      den += __shfl_xor_sync(0xffffffffu, den, o);
-    }
-    __syncwarp();  // every lane has read row l of this head's q slice before it is overwritten
-    if (g == 0) sm[0][l][hb + e] = num * (1.f / (den + eps)) * (float)S;
+    float num = qa.x * kv[0];
+    num = fmaf(qa.y, kv[1], num); num = fmaf(qa.z, kv[2], num); num = fmaf(qa.w, kv[3], num);
+    num = fmaf(qb.x, kv[4], num); num = fmaf(qb.y, kv[5], num); num = fmaf(qb.z, kv[6], num); num = fmaf(qb.w, kv[7], num);
+    num += __shfl_xor_sync(0xffffffffu, num, D);
+    const float zl = __shfl_sync(0xffffffffu, z, l);
+    if (g == 0) sm[1][l][hb + e] = num * zl;
   }
   __syncthreads();
-  for (int idx = t; idx < L * C4; idx += NT) {
-    const int r = idx / C4, c4 = idx % C4;
-    reinterpret_cast<float4*>(out + ((size_t)n * L + r) * ldo)[c4] = reinterpret_cast<const float4*>(&sm[0][r][0])[c4];
-  }
+  for (int r = r0; r < L; r += rstep)
+    reinterpret_cast<float4*>(out + ((size_t)n * L + r) * ldo)[c4] = reinterpret_cast<const float4*>(&sm[1][r][0])[c4];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
