@@ -134,6 +134,101 @@ __global__ void __launch_bounds__(kTileThreads, 2) linear_simt_kernel(LinearArgs
   }
 }
 
+// ---------------------------------------------------------------------------------------------- skinny M (<= 32) split-K
+// The FAR gate / encoder MLPs are [32 pairs] x [35840 (+22)] x [512]: 73 MB of weights per call, 12 us of HBM time.  The
+// 128 x 128 tile kernel above computes 128 rows for 32 (FMA-bound on padding: ~300 us per call); here the tile is
+// 32 rows x 128 columns x 32 k, thread = 4 rows x 4 columns, operands transposed into shared memory with an XOR swizzle of
+// the 4-column groups (conflict-free scalar stores and float4 loads), register double buffering of the next k-slab.
+constexpr int SK_BM = 32, SK_BN = 128, SK_BK = 32;
+struct __align__(16) SkinnySmem {
+  float a[2][SK_BK][SK_BM];
+  float b[2][SK_BK][SK_BN];
+};  // 40 KiB
+
+template <bool kVec4>
+__device__ __forceinline__ void skinny_tile_mma(const float* __restrict__ A, int lda, int mValid,
+                                                const float* __restrict__ B, int ldb, int nValid, int K,
+                                                SkinnySmem& sm, float (&acc)[4][4]) {
+  const int t = threadIdx.x;
+  const int k4 = t & 7, lr = t >> 3;          // loader: float4 column k4 of rows lr (+32 i)
+  const int tm = t >> 5, tn = t & 31;         // compute: rows 4 tm .. +3, columns 4 tn .. +3
+  const int nk = (K + SK_BK - 1) / SK_BK;
+  if (nk == 0) return;
+  float4 ra, rb[4];
+  auto fetch = [&](int kt) {
+    const int k = kt * SK_BK + k4 * 4;
+    ra = tile_ld4<kVec4>(A, lda, lr, mValid, k, K);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rb[i] = tile_ld4<kVec4>(B, ldb, lr + 32 * i, nValid, k, K);
+  };
+  auto stash = [&](int buf) {
+    // element (row r, k) lives at [k][4 * ((r >> 2) ^ (k >> 2 & 7)) + (r & 3)]
+    const int ga = ((lr >> 2) ^ k4) * 4 + (lr & 3);
+    sm.a[buf][k4 * 4 + 0][ga] = ra.x; sm.a[buf][k4 * 4 + 1][ga] = ra.y;
+    sm.a[buf][k4 * 4 + 2][ga] = ra.z; sm.a[buf][k4 * 4 + 3][ga] = ra.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = lr + 32 * i;
+      const int gb = ((r >> 2) ^ k4) * 4 + (r & 3);
+      sm.b[buf][k4 * 4 + 0][gb] = rb[i].x; sm.b[buf][k4 * 4 + 1][gb] = rb[i].y;
+      sm.b[buf][k4 * 4 + 2][gb] = rb[i].z; sm.b[buf][k4 * 4 + 3][gb] = rb[i].w;
+    }
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    const bool more = kt + 1 < nk;
+    if (more) fetch(kt + 1);
+#pragma unroll
+    for (int k = 0; k < SK_BK; ++k) {
+      const int sw = (k >> 2) & 7;
+      const float4 a4 = *reinterpret_cast<const float4*>(&sm.a[cur][k][(tm ^ sw) * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&sm.b[cur][k][(tn ^ sw) * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) stash(cur ^ 1);
+    __syncthreads();
+  }
+}
+
+// grid (ceil(N / 128), 1, splits): partial products of split z into ws[z][M][N]; splitk_reduce_kernel finishes.
+template <bool kVec4>
+__global__ void __launch_bounds__(256, 3) linear_skinny_kernel(LinearArgs p) {
+  __shared__ SkinnySmem sm;
+  const int n0 = blockIdx.x * SK_BN, z = blockIdx.z;
+  const int nValid = min(SK_BN, p.N - n0);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int kbeg = z * p.kchunk;
+  int klen = min(p.kchunk, p.K1 - kbeg);
+  if (klen < 0) klen = 0;
+  skinny_tile_mma<kVec4>(p.x1 + kbeg, p.ldx1, p.M, p.W + (size_t)n0 * p.ldw + kbeg, p.ldw, nValid, klen, sm, acc);
+  if (p.x2 != nullptr && p.K2 > 0 && z == p.splits - 1)   // K-concat tail rides with the last split
+    skinny_tile_mma<kVec4>(p.x2, p.ldx2, p.M, p.W + (size_t)n0 * p.ldw + p.K1, p.ldw, nValid, p.K2, sm, acc);
+  const int tm = threadIdx.x >> 5, tn = threadIdx.x & 31;
+  float* out = p.ws + (size_t)z * p.M * p.N;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = tm * 4 + i;
+    if (r >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tn * 4 + j;
+      if (c < p.N) out[(size_t)r * p.N + c] = acc[i][j];
+    }
+  }
+}
+
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ bias,
                                      float* __restrict__ y, int ldy, int M, int N, int act, int act_cols) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -394,6 +489,29 @@ int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int l
   }
   const bool vec = ptr_aligned16(x1) && ptr_aligned16(W) && (ldx1 % 4 == 0) && (ldw % 4 == 0) && (K1 % 4 == 0) &&
                    (x2 == nullptr || (ptr_aligned16(x2) && ldx2 % 4 == 0 && K2 % 4 == 0));
+  // skinny problems (M <= 32 rows, long K: the 35840-wide FAR MLPs): 32-row tiles, more splits (FAR_SKINNY=0 disables)
+  static const bool skinny_on = !(getenv("FAR_SKINNY") && getenv("FAR_SKINNY")[0] == '0');
+  if (skinny_on && M <= SK_BM && K1 >= 2048 && rowbias == nullptr && workspace != nullptr) {
+    const int ntiles = ceil_div(N, SK_BN);
+    int s2 = (3 * kNumSMs) / ntiles;
+    if (s2 > K1 / 256) s2 = K1 / 256;
+    if (s2 > 128) s2 = 128;
+    if (s2 < 2) s2 = 2;
+    const int kc2 = ceil_div(ceil_div(K1, s2), SK_BK) * SK_BK;
+    s2 = ceil_div(K1, kc2);
+    if (s2 >= 2 && workspace_bytes >= (size_t)s2 * M * N * sizeof(float)) {
+      p.splits = s2; p.kchunk = kc2; p.ws = workspace;
+      dim3 g2(ntiles, 1, s2);
+      ProfScope prof(PROF_LINEAR_SIMT, 2.0 * M * N * (K1 + K2), 4.0 * ((double)M * (K1 + K2) + (double)N * (K1 + K2) + (double)M * N), st);
+      if (vec) linear_skinny_kernel<true><<<g2, 256, 0, st>>>(p);
+      else linear_skinny_kernel<false><<<g2, 256, 0, st>>>(p);
+      FAR_CHECK_LAUNCH();
+      const long long tot = (long long)M * N;
+      splitk_reduce_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(p.ws, p.splits, bias, y, ldy, M, N, act, act_cols);
+      FAR_CHECK_LAUNCH();
+      return FAR_OK;
+    }
+  }
   dim3 grid(ceil_div(N, TBN), ceil_div(M, TBM), p.splits);
   ProfScope prof(PROF_LINEAR_SIMT, 2.0 * M * N * (K1 + K2), 4.0 * ((double)M * (K1 + K2) + (double)N * (K1 + K2) + (double)M * N), st);
   if (vec)
@@ -471,6 +589,10 @@ extern "C" size_t far_linear_workspace_bytes(int M, int N, int K) {
   int s, kc;
   choose_splits(M, N, K, &s, &kc);
   size_t b = (s > 1) ? (size_t)s * M * N * sizeof(float) : 0;
+  if (M <= SK_BM && K >= 2048) {   // skinny split-K path: up to 128 splits
+    const size_t b2 = (size_t)128 * M * N * sizeof(float);
+    if (b2 > b) b = b2;
+  }
   size_t tcb = tc_linear_workspace_bytes(M, N, K);
   return (b > tcb ? b : tcb) + 256;
 }

@@ -38,6 +38,20 @@ def test_linear(M, N, K, act):
     assert_close(y, ref, 2e-5, 1e-5, f"linear {M}x{N}x{K} act{act}")
 
 
+@pytest.mark.parametrize("M,N,K,K2", [(32, 512, 35840, 0), (32, 512, 35840, 24), (7, 130, 4100, 20), (1, 512, 2048, 0),
+                                      (32, 9, 2304, 0)])
+def test_linear_skinny_split_k(M, N, K, K2):
+    """The M <= 32, long-K path (linear_skinny_kernel: the 35840-wide FAR encoder / gate MLPs, transformer.py:259-264),
+    with the short K-concat tail of the gates, against fp64."""
+    g = O.rng(M + N + K + K2)
+    x, w, b = O.randn(g, M, K), O.randn(g, N, K + K2, scale=(K + K2) ** -0.5), O.randn(g, N, scale=0.1)
+    x2 = O.randn(g, M, K2) if K2 else None
+    y = ops.linear(cu(x), cu(w), cu(b), ACT_RELU, x2=cu(x2) if K2 else None, engine=ENGINE_SIMT)
+    xin = torch.cat([x, x2], -1) if K2 else x
+    ref = torch.relu(torch.nn.functional.linear(xin.double(), w.double(), b.double()))
+    assert_close(y, ref, 2e-5, 1e-5, f"skinny linear {M}x{N}x{K}+{K2}")
+
+
 def test_linear_two_segments_and_tail():
     """[x1 | x2] K-segments (mlp.0 on cat[x, message]) and an unaligned tail (moe_predictor: 35840 + 22)."""
     g = O.rng(3)
