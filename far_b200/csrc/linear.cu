@@ -229,69 +229,6 @@ __global__ void __launch_bounds__(256, 3) linear_skinny_kernel(LinearArgs p) {
   }
 }
 
-// Row-streaming variant for 16-byte-aligned operands: the tile kernels read a 128-byte sliver of each of 128 weight rows
-// per k-slab (rows are 143 KB apart: one DRAM page activation per 128 bytes).  Here a warp owns TWO weight rows and
-// streams them along K in 2 KB runs (512 floats per visit: whole DRAM pages, 32 KB of loads in flight per CTA); the 32
-// activation rows of the current 512-wide k-chunk sit in shared memory (64 KB) and are shared by the CTA's 16 weight rows.
-// Lane accumulators [2 rows][32 m] are reduced across the warp once at the end.  Virtual K = [x1 | x2].
-constexpr int RW_ROWS = 16, RW_KC = 512;
-constexpr size_t RW_SMEM = (size_t)SK_BM * RW_KC * sizeof(float);
-
-__global__ void __launch_bounds__(256, 2) linear_rowwise_kernel(LinearArgs p) {
-  extern __shared__ __align__(16) float rw_xs[];   // [32][RW_KC]
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int n0 = blockIdx.x * RW_ROWS + 2 * w, z = blockIdx.z;
-  const int Kt = p.K1 + p.K2;
-  const int kbeg = z * p.kchunk, kend = min(Kt, kbeg + p.kchunk);
-  const bool r0ok = n0 < p.N, r1ok = n0 + 1 < p.N;
-  const float* w0p = p.W + (size_t)(r0ok ? n0 : 0) * p.ldw;
-  const float* w1p = p.W + (size_t)(r1ok ? n0 + 1 : 0) * p.ldw;
-  float acc0[SK_BM], acc1[SK_BM];
-#pragma unroll
-  for (int m = 0; m < SK_BM; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
-  for (int kc0 = kbeg; kc0 < kend; kc0 += RW_KC) {
-    // stage x[:, kc0 : kc0 + RW_KC) (zero beyond M rows / beyond kend)
-    for (int idx = t; idx < SK_BM * (RW_KC / 4); idx += 256) {
-      const int m = idx / (RW_KC / 4), c4 = idx % (RW_KC / 4), k = kc0 + 4 * c4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < p.M && k < kend)
-        v = (k < p.K1) ? __ldg(reinterpret_cast<const float4*>(p.x1 + (size_t)m * p.ldx1 + k))
-                       : __ldg(reinterpret_cast<const float4*>(p.x2 + (size_t)m * p.ldx2 + (k - p.K1)));
-      reinterpret_cast<float4*>(rw_xs)[idx] = v;
-    }
-    __syncthreads();
-    float4 wa[4], wb[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {   // all eight 16-byte loads of this lane in flight before the first use
-      const int k = kc0 + 4 * (lane + 32 * j);
-      wa[j] = (r0ok && k < kend) ? __ldcs(reinterpret_cast<const float4*>(w0p + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      wb[j] = (r1ok && k < kend) ? __ldcs(reinterpret_cast<const float4*>(w1p + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4* xr = reinterpret_cast<const float4*>(rw_xs) + lane + 32 * j;
-#pragma unroll
-      for (int m = 0; m < SK_BM; ++m) {
-        const float4 x4 = xr[m * (RW_KC / 4)];
-        acc0[m] = fmaf(wa[j].x, x4.x, acc0[m]); acc0[m] = fmaf(wa[j].y, x4.y, acc0[m]);
-        acc0[m] = fmaf(wa[j].z, x4.z, acc0[m]); acc0[m] = fmaf(wa[j].w, x4.w, acc0[m]);
-        acc1[m] = fmaf(wb[j].x, x4.x, acc1[m]); acc1[m] = fmaf(wb[j].y, x4.y, acc1[m]);
-        acc1[m] = fmaf(wb[j].z, x4.z, acc1[m]); acc1[m] = fmaf(wb[j].w, x4.w, acc1[m]);
-      }
-    }
-    __syncthreads();
-  }
-  float* out = p.ws + (size_t)z * p.M * p.N;
-#pragma unroll
-  for (int m = 0; m < SK_BM; ++m) {
-    const float s0 = warp_sum(acc0[m]), s1 = warp_sum(acc1[m]);
-    if (lane == 0 && m < p.M) {
-      if (r0ok) out[(size_t)m * p.N + n0] = s0;
-      if (r1ok) out[(size_t)m * p.N + n0 + 1] = s1;
-    }
-  }
-}
-
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ bias,
                                      float* __restrict__ y, int ldy, int M, int N, int act, int act_cols) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -554,29 +491,6 @@ int linear_dispatch_rb(const float* x1, int ldx1, int K1, const float* x2, int l
                    (x2 == nullptr || (ptr_aligned16(x2) && ldx2 % 4 == 0 && K2 % 4 == 0));
   // skinny problems (M <= 32 rows, long K: the 35840-wide FAR MLPs): 32-row tiles, more splits (FAR_SKINNY=0 disables)
   static const bool skinny_on = !(getenv("FAR_SKINNY") && getenv("FAR_SKINNY")[0] == '0');
-  if (skinny_on && vec && M <= SK_BM && K1 >= 2048 && rowbias == nullptr && workspace != nullptr) {
-    // row-streaming kernel: virtual K = K1 + K2 split into multiples of the 512-wide chunk, ~2.5 CTAs per SM
-    const int Kt = K1 + K2, ngroups = ceil_div(N, RW_ROWS);
-    int s3 = ceil_div(5 * kNumSMs / 2, ngroups);
-    if (s3 > ceil_div(Kt, RW_KC)) s3 = ceil_div(Kt, RW_KC);
-    if (s3 > 128) s3 = 128;
-    if (s3 < 1) s3 = 1;
-    const int kc3 = ceil_div(ceil_div(Kt, s3), RW_KC) * RW_KC;
-    s3 = ceil_div(Kt, kc3);
-    if (workspace_bytes >= (size_t)s3 * M * N * sizeof(float)) {
-      static bool attr[64] = {};
-      if (first_use_on_device(attr))
-        cudaFuncSetAttribute(linear_rowwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RW_SMEM);
-      p.splits = s3; p.kchunk = kc3; p.ws = workspace;
-      ProfScope prof(PROF_LINEAR_SIMT, 2.0 * M * N * Kt, 4.0 * ((double)M * Kt + (double)N * Kt + (double)M * N), st);
-      linear_rowwise_kernel<<<dim3(ngroups, 1, s3), 256, RW_SMEM, st>>>(p);
-      FAR_CHECK_LAUNCH();
-      const long long tot = (long long)M * N;
-      splitk_reduce_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(p.ws, p.splits, bias, y, ldy, M, N, act, act_cols);
-      FAR_CHECK_LAUNCH();
-      return FAR_OK;
-    }
-  }
   if (skinny_on && M <= SK_BM && K1 >= 2048 && rowbias == nullptr && workspace != nullptr) {
     const int ntiles = ceil_div(N, SK_BN);
     int s2 = (3 * kNumSMs) / ntiles;
