@@ -1,11 +1,13 @@
 // tcgen05 3xTF32 GEMM with the A operand in TENSOR MEMORY (raw fp32 activations):  C = act(A B^T + bias).
 //
-// Why: tc_gemm_kernel (SS operands) is paced by the 128 B/clk shared-memory port, not by the tensor pipe
-// (profiles/r1_mma_rate_microbench.md): per 32-wide k-block it moves 176 KB through shared memory (TMA fills 48, the hi/lo
-// converter 32, UMMA operand reads 80, epilogue staging 16) against 768 cycles of MMA math.  Here the converter warps read
-// the landed raw A tile ONCE (16 KB) and write hi and lo straight into TMEM with tcgen05.st; all MMAs take A from TMEM
-// (TS form), so the port only carries the TMA fills (48), that one read (16), the B operand reads (48) and the epilogue
-// staging (16) = 128 KB per k-block, and the freed 16 KB A_lo slot buys a 4th pipeline stage.
+// Why: in tc_gemm_kernel (SS operands) every 32-wide k-block moves 176 KB through shared memory (TMA fills 48, the hi/lo
+// converter 32, UMMA operand reads 80, epilogue staging 16) against 768 cycles of MMA math
+// (profiles/r1_mma_rate_microbench.md).  Here the converter warps read the landed raw A tile ONCE (16 KB) and write hi and lo
+// straight into TMEM with tcgen05.st; all MMAs take A from TMEM (TS form), so the port only carries the TMA fills (48),
+// that one read (16), the B operand reads (48) and the epilogue staging (16) = 128 KB per k-block, and the freed 16 KB
+// A_lo slot buys a 4th pipeline stage.  Measured (profiles/r3_gemm_engine_study.md): 2-6 % faster than the SS kernel back
+// to back under the power cap, tensor pipe 60-74 % active under ncu (SS: 57-71 %); what is left is the L2 -> SM fill of
+// 48 KB per k-block, the epilogue's interference with the next tile's MMAs and the global stores (13 %).
 //
 // TMEM columns (512): main0 [0,128) | cross [128,256) | main1 [256,384) | A ring: 2 stages x (hi 32 | lo 32) [384,512).
 // The main accumulator is double buffered (epilogue of tile t overlaps the main loop of tile t+1); the 2^-11-times-smaller
