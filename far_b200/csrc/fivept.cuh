@@ -73,9 +73,10 @@ __device__ inline int real_roots_deg10(const double* c, double* roots) {
     zr[k] = r0 * cos(ang) * (1.0 + 0.02 * k);
     zi[k] = r0 * sin(ang) * (1.0 + 0.02 * k);
   }
-  for (int it = 0; it < 64; ++it) {   // typically 15-25 iterations; the Gauss-Newton polish in solve() restores the last digits
-    double maxstep = 0.0;
+  unsigned live = (1u << deg) - 1u;   // roots still moving: a converged root is frozen (its update is skipped)
+  for (int it = 0; it < 64 && live; ++it) {   // typically 15-25 iterations; solve()'s Gauss-Newton polish restores the last digits
     for (int k = 0; k < deg; ++k) {
+      if (!(live >> k & 1u)) continue;
       // Horner for p and p' at z_k
       double pr = c[deg], pi = 0.0, dr = 0.0, di = 0.0;
       for (int j = deg - 1; j >= 0; --j) {
@@ -87,24 +88,25 @@ __device__ inline int real_roots_deg10(const double* c, double* roots) {
       const double dn = dr * dr + di * di;
       if (!(dn > 0.0)) continue;
       // w = p / p'
-      const double wr = (pr * dr + pi * di) / dn, wi = (pi * dr - pr * di) / dn;
+      const double idn = 1.0 / dn;
+      const double wr = (pr * dr + pi * di) * idn, wi = (pi * dr - pr * di) * idn;
       // s = sum_{j != k} 1 / (z_k - z_j)
       double sr = 0.0, si = 0.0;
       for (int j = 0; j < deg; ++j) {
         if (j == k) continue;
         const double er = zr[k] - zr[j], ei = zi[k] - zi[j];
         const double en = er * er + ei * ei;
-        if (en > 0.0) { sr += er / en; si -= ei / en; }
+        if (en > 0.0) { const double ien = 1.0 / en; sr = fma(er, ien, sr); si = fma(-ei, ien, si); }
       }
       // step = w / (1 - w s)
       const double qr = 1.0 - (wr * sr - wi * si), qi = -(wr * si + wi * sr);
       const double qn = qr * qr + qi * qi;
       if (!(qn > 0.0)) continue;
-      const double stepr = (wr * qr + wi * qi) / qn, stepi = (wi * qr - wr * qi) / qn;
+      const double iqn = 1.0 / qn;
+      const double stepr = (wr * qr + wi * qi) * iqn, stepi = (wi * qr - wr * qi) * iqn;
       zr[k] -= stepr; zi[k] -= stepi;
-      maxstep = fmax(maxstep, (fabs(stepr) + fabs(stepi)) / (1.0 + fabs(zr[k]) + fabs(zi[k])));
+      if ((fabs(stepr) + fabs(stepi)) < 1e-13 * (1.0 + fabs(zr[k]) + fabs(zi[k]))) live &= ~(1u << k);
     }
-    if (maxstep < 1e-12) break;
   }
   int n = 0;
   for (int k = 0; k < deg; ++k) {
