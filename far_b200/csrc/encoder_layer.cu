@@ -124,9 +124,23 @@ extern "C" int far_loftr_encoder_layer(const float* x, const float* source, floa
     TcLinearEx c{};
     c.x1 = q; c.ldx1 = C; c.K1 = C; c.Whi = bhi; c.Wlo = blo; c.wlo_is_cat = cat ? 1 : 0; c.b_grouped = 1; c.y = msg; c.ldy = C; c.M = ML; c.N = C;
     c.act = FAR_ACT_NONE; c.act_cols = -1; c.G = N; c.L = L; c.workspace = lw; c.workspace_bytes = lwb;
+    // norm1 without a pass of its own: the `message` GEMM's epilogue leaves per-(row, 32-column) (mean, M2) partials in
+    // the (now free) attn slot and the mlp.0 GEMM's converter threads normalise its second A segment on the fly
+    const bool ln_fused = tc_ln_fusion_available() && C % 32 == 0 && ps_wmlp0 != nullptr;
+    if (ln_fused) c.ln_stats_out = attn;
     if ((rc = tc_linear_ex(c, st))) return rc;
-    if ((rc = far_layernorm(msg, w->g1, w->b1, nullptr, attn, ML, C, eps1, stream))) return rc;  // attn := LN(msg)
-    if ((rc = linear_dispatch_ps(x, C, C, attn, C, C, w->wmlp0, 2 * C, ps_wmlp0, hid, 2 * C, ML, 2 * C, FAR_ACT_RELU, -1, engine, lw, lwb, st))) return rc;
+    if (ln_fused) {
+      TcLinearEx d{};
+      d.x1 = x; d.ldx1 = C; d.K1 = C; d.x2 = msg; d.ldx2 = C; d.K2 = C; d.W = w->wmlp0; d.ldw = 2 * C;
+      d.Whi = ps_wmlp0; d.Wlo = ps_lo(ps_wmlp0, 2 * C, 2 * C);
+      d.y = hid; d.ldy = 2 * C; d.M = ML; d.N = 2 * C; d.act = FAR_ACT_RELU; d.act_cols = -1;
+      d.ln_stats_in = attn; d.ln_gamma = w->g1; d.ln_beta = w->b1; d.ln_eps = eps1;
+      d.workspace = lw; d.workspace_bytes = lwb;
+      if ((rc = tc_linear_ex(d, st))) return rc;
+    } else {
+      if ((rc = far_layernorm(msg, w->g1, w->b1, nullptr, attn, ML, C, eps1, stream))) return rc;  // attn := LN(msg)
+      if ((rc = linear_dispatch_ps(x, C, C, attn, C, C, w->wmlp0, 2 * C, ps_wmlp0, hid, 2 * C, ML, 2 * C, FAR_ACT_RELU, -1, engine, lw, lwb, st))) return rc;
+    }
     if ((rc = linear_dispatch_ps(hid, 2 * C, 2 * C, nullptr, 0, 0, w->wmlp2, 2 * C, ps_wmlp2, msg, C, ML, C, FAR_ACT_NONE, -1, engine, lw, lwb, st))) return rc;
     return far_layernorm(msg, w->g2, w->b2, x, out, ML, C, eps2, stream);
   }

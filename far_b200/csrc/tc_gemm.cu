@@ -414,6 +414,15 @@ size_t tc_linear_workspace_need(const float* x1, int ldx1, int K1, const float* 
   return (raw_a_ok(x1, ldx1, K1, x2, ldx2, K2) ? 0 : 2 * tc::al((size_t)M * K * 4)) + 2 * tc::al((size_t)N * K * 4) + 2048;
 }
 
+static int tc_ts_mode() {
+  static const int m = getenv("FAR_TC_TS") ? atoi(getenv("FAR_TC_TS")) : 1;
+  return m;
+}
+bool tc_ln_fusion_available() {
+  static const bool off = getenv("FAR_LN_FUSION") && getenv("FAR_LN_FUSION")[0] == '0';
+  return !off && tc_ts_mode() == 1 && !tc::tc_cross16_on();
+}
+
 int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
   using namespace tc;
   const int K = a.K1 + a.K2, M = a.M, N = a.N;
@@ -501,7 +510,14 @@ int tc_linear_ex(const TcLinearEx& a, cudaStream_t st) {
   // raw fp32 activations: the A operand goes through TMEM.  FAR_TC_TS = 1 (default): one CTA per 128 x 128 tile
   // (tc_gemm_ts.cu); 2: CTA pairs sharing B (tc_gemm_pair.cu: 13 % faster than mode 1 at ~1.1 GHz SM clock, 15-30 % slower at
   // the 1.5-1.7 GHz of the power-capped step); 0: the all-shared-memory kernel below
-  static const int ts_mode = getenv("FAR_TC_TS") ? atoi(getenv("FAR_TC_TS")) : 1;
+  const int ts_mode = tc_ts_mode();
+  if (a.ln_stats_in != nullptr &&
+      !(rawA && !cross16 && ts_mode == 1 && a.x2 != nullptr && a.K2 % 32 == 0 && a.ln_gamma && a.ln_beta))
+    return FAR_ERR_ARG;   // only the TMEM-operand kernel normalises its second A segment
+  if (a.ln_stats_out != nullptr && N % 32 != 0) return FAR_ERR_ARG;
+  p.ln_out = reinterpret_cast<float2*>(a.ln_stats_out);
+  p.ln_in = reinterpret_cast<const float2*>(a.ln_stats_in);
+  p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps; p.ln_chunks = a.K2 / 32;
   const int pair_clusters = (rawA && !cross16 && ts_mode >= 2) ? gemm_pair_max_clusters() : 0;
   if (pair_clusters > 0) {
     CUtensorMap mBhi2, mBlo2;   // 64-row boxes: each CTA of a pair loads its half of the 128 B rows

@@ -35,7 +35,13 @@ struct TcLinearEx {
   const float* ksum; int ksum_rec, ksum_off; float eps;  // act == ELU1 and ksum != nullptr: y = (elu(x)+1) * Z,
                                     // Z[row, h] = 1 / (dot(y[row, 32h:32h+32], ksum[(g*N/32 + h)*ksum_rec + ksum_off : +32]) + eps)
   const float* rowbias; int rowbias_group;  // optional: + rowbias[(row / rowbias_group) * N + col]
+  // LayerNorm fused across two GEMMs (tc_gemm_epi.cuh GemmArgs::ln_*): ln_stats_out [M][N/32][2] written by this GEMM's
+  // epilogue (N % 32 == 0); ln_stats_in [M][K2/32][2] + gamma / beta [K2]: x2 is normalised on the fly (TS kernel only)
+  float* ln_stats_out;
+  const float* ln_stats_in; const float* ln_gamma; const float* ln_beta; float ln_eps;
   float* workspace; size_t workspace_bytes;
 };
 int tc_linear_ex(const TcLinearEx& a, cudaStream_t st);
+// whether tc_linear_ex can take ln_stats_in (the TMEM-operand kernel is the active GEMM kernel)
+bool tc_ln_fusion_available();
 }  // namespace far

@@ -30,6 +30,12 @@ struct GemmArgs {
   int kb1;          // raw-A: number of 32-wide k-blocks that come from x1 (= K1 / 32)
   const float* ksum; int ksum_rec, ksum_off, heads; float eps;  // ACT_ELU1Z: Ksum[(g*heads + h)*ksum_rec + ksum_off + d]
   const float* rowbias; int rb_group;  // + rowbias[(row / rb_group) * N + col]  (fine_preprocess: per-match coarse term)
+  // LayerNorm fused across two GEMMs (encoder_layer.cu: norm1 between `message` and mlp.0): the producer's epilogue writes
+  // per (row, 32-column block) the block mean and M2 = sum (v - mean)^2 (ln_out [M][N/32]); the consumer (tc_gemm_ts_kernel
+  // only) combines a row's ln_chunks partials (Chan) and its converter threads apply (v - mu) rstd gamma + beta to the
+  // k-blocks of the SECOND A segment before the hi/lo split.
+  float2* ln_out;
+  const float2* ln_in; const float* ln_gamma; const float* ln_beta; float ln_eps; int ln_chunks;
   int cross16;      // raw-A only: slot 1 = A_cat, slot 3 = B_cat, cross terms as bf16 MMAs (tc_common.cuh)
   int dbg;          // diagnostics (env FAR_TC_DBG): 1 = skip global stores, 2 = skip the epilogue body, 4 = skip MMAs
 };
@@ -143,6 +149,16 @@ __device__ __forceinline__ void epi_block(float (&t)[32], const GemmArgs& p, con
           if (col < actc) t[e] = apply_act(t[e], p.act == ACT_ELU1Z ? FAR_ACT_ELU1 : p.act);
         }
       }
+    }
+    if (p.ln_out != nullptr && col0 + 32 <= p.N && r0 + quarter * 32 + lane < p.L) {
+      float sum = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) sum += t[e];
+      const float mean = sum * (1.f / 32.f);
+      float m2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) { const float d = t[e] - mean; m2 = fmaf(d, d, m2); }
+      p.ln_out[(size_t)grow * (p.N >> 5) + (col0 >> 5)] = make_float2(mean, m2);
     }
     if (trace) trace[0] = clock64();   // bias / activation done
     // the previous TMA store of this warp must have finished READING the staging tile

@@ -202,16 +202,42 @@ tc_gemm_ts_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_consta
     uint32_t phase = 0, aphase = 0;
     long long w_full = 0, w_afree = 0, t_begin = TS_CLK();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      float ln_mu = 0.f, ln_rstd = 0.f;
+      if (p.ln_in != nullptr) {   // this row's LayerNorm statistics from the producer's per-block partials (Chan's update)
+        const int tm = tile / tiles_n;
+        const int g = tm / tiles_pg, lrow = (tm % tiles_pg) * BM + row;
+        if (lrow < p.L) {
+          const float2* st = p.ln_in + ((size_t)g * p.L + lrow) * p.ln_chunks;
+          float n = 0.f, mean = 0.f, m2 = 0.f;
+          for (int c = 0; c < p.ln_chunks; ++c) {
+            const float2 pc = __ldg(st + c);
+            const float tot = n + 32.f, delta = pc.x - mean;
+            mean = fmaf(delta, 32.f / tot, mean);
+            m2 += pc.y + delta * delta * (n * 32.f / tot);
+            n = tot;
+          }
+          ln_mu = mean;
+          ln_rstd = rsqrtf(m2 / n + p.ln_eps);
+        }
+      }
       for (int kb = 0; kb < kblocks; ++kb) {
         const long long c0 = TS_CLK();
         mbar_wait(full_bar(stage), phase);
         w_full += TS_CLK() - c0;
         const float4* arow = reinterpret_cast<const float4*>(smem_dyn + (base + stage * TS_STAGE_BYTES - raw) + row * 128);
         uint32_t hi[32], lo[32];
+        const bool ln_here = p.ln_in != nullptr && kb >= p.kb1;   // second A segment: LayerNorm applied on the fly
+        const float4* lg = reinterpret_cast<const float4*>(p.ln_gamma) + (ln_here ? (kb - p.kb1) * 8 : 0);
+        const float4* lb = reinterpret_cast<const float4*>(p.ln_beta) + (ln_here ? (kb - p.kb1) * 8 : 0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {   // 16-byte chunk j of row r sits at chunk j ^ (r & 7) (SWIZZLE_128B)
           const float4 v = arow[j ^ sw];
-          const float x[4] = {v.x, v.y, v.z, v.w};
+          float x[4] = {v.x, v.y, v.z, v.w};
+          if (ln_here) {
+            const float4 gm = __ldg(lg + j), bt = __ldg(lb + j);
+            x[0] = fmaf((x[0] - ln_mu) * ln_rstd, gm.x, bt.x); x[1] = fmaf((x[1] - ln_mu) * ln_rstd, gm.y, bt.y);
+            x[2] = fmaf((x[2] - ln_mu) * ln_rstd, gm.z, bt.z); x[3] = fmaf((x[3] - ln_mu) * ln_rstd, gm.w, bt.w);
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const uint32_t h = __float_as_uint(x[e]) & 0xFFFFE000u;
